@@ -1,0 +1,286 @@
+"""Host side of the Flood-complex path: the reference's public API on top of the sm_100a kernels.
+
+``flood_complex`` and ``generate_landmarks`` keep the signatures, argument meaning, return types
+and exceptions of ``flooder/core.py:32-43`` and ``:291-296`` of the reference.  What differs is
+everything between "list of Delaunay simplices" and "per-simplex filtration values": it runs in
+``libflood_b200.so`` (see ``include/flood_b200.h``) through the torch extension
+``flooder_b200._native.ext()``.  There is no CPU, Triton or eager-PyTorch fallback: inputs that
+are not on a CUDA device are rejected.
+"""
+from __future__ import annotations
+
+import functools
+import itertools
+import os
+import warnings
+from numbers import Integral
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native
+from . import distributed as fdist
+from .simplex_tree import HAS_GUDHI, SimplexTree, delaunay_simplex_tree
+
+_SUPPORTED_DTYPES = (torch.float32, torch.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+# sample-point generators (host, tiny) -- same weights as the reference
+# ----------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=32)
+def _lattice(n: int, dim: int) -> np.ndarray:
+    """Integer barycentric lattice: all (dim+1)-part compositions of n-1 in the order of
+    ``itertools.combinations`` over bar positions (reference ``core.py:369-380``)."""
+    bars = np.fromiter(
+        itertools.chain.from_iterable(itertools.combinations(range(n + dim - 1), dim)), dtype=np.int64
+    ).reshape(-1, dim)
+    edge = np.empty((bars.shape[0], dim + 2), dtype=np.int64)
+    edge[:, 0] = -1
+    edge[:, 1:-1] = bars
+    edge[:, -1] = n + dim - 1
+    return np.diff(edge, axis=1) - 1
+
+
+def generate_grid(n: int, dim: int, device, dtype=torch.float32):
+    """Grid of ``n`` points per edge on the unit ``dim``-simplex (reference ``core.py:346-402``).
+
+    Returns ``(weights (C, dim+1), vertex_idxs, face_idxs)`` with the reference's meaning:
+    ``face_idxs[k][j]`` are the rows whose weights vanish on the j-th ``k``-subset of vertices,
+    ``vertex_idxs[k][j]`` the remaining vertex positions.
+    """
+    counts = _lattice(int(n), int(dim))
+    axes = np.arange(dim + 1)
+    face_idxs, vertex_idxs = [], []
+    for k in range(dim + 1):
+        rows_k, verts_k = [], []
+        for zero_set in itertools.combinations(range(dim + 1), k):
+            sel = np.ones(len(counts), dtype=bool) if k == 0 else (counts[:, list(zero_set)] == 0).all(axis=1)
+            rows_k.append(torch.as_tensor(np.nonzero(sel)[0], device=device))
+            verts_k.append(torch.as_tensor(axes[~np.isin(axes, zero_set)], device=device))
+        face_idxs.append(torch.stack(rows_k))
+        vertex_idxs.append(torch.stack(verts_k))
+    weights = torch.empty((counts.shape[0], dim + 1), dtype=dtype, device=device)
+    torch.divide(torch.as_tensor(counts, device=device), n - 1, out=weights)
+    return weights, vertex_idxs, face_idxs
+
+
+def generate_uniform_weights(num_rand: int, dim: int, device, dtype=torch.float32) -> torch.Tensor:
+    """Uniform (Dirichlet(1,..,1)) weights on the unit simplex (reference ``core.py:405-427``);
+    drawn on the CPU from torch's global generator so that CPU and GPU callers see the same
+    stream."""
+    if dim == 0:
+        return torch.ones((num_rand, 1), device=device, dtype=dtype)
+    w = -torch.log(1 - torch.rand(num_rand, dim + 1)).to(device, dtype=dtype)
+    return w / w.sum(dim=1, keepdim=True)
+
+
+def _support_masks(weights: torch.Tensor) -> torch.Tensor:
+    """bit k of mask[r] <=> weights[r, k] != 0."""
+    K = weights.shape[1]
+    bits = (weights != 0).to(torch.int32) << torch.arange(K, device=weights.device, dtype=torch.int32)
+    return bits.sum(dim=1).to(torch.int32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# landmarks
+# ----------------------------------------------------------------------------------------------
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if t.device.type != "cuda":
+        raise RuntimeError(
+            f"Device not supported: {what} is on '{t.device}'. flooder_b200 runs on CUDA (sm_100a) "
+            "devices only and has no CPU fallback."
+        )
+
+
+def fps_indices(points: torch.Tensor, n_lms: int, start_idx: int = 0) -> torch.Tensor:
+    """Indices chosen by exact farthest-point sampling, int64 on ``points.device``."""
+    _require_cuda(points, "points")
+    pts32 = points.detach().to(torch.float32).contiguous()
+    return _native.ext().fps(pts32, int(n_lms), int(start_idx))
+
+
+def generate_landmarks(
+    points: torch.Tensor,
+    n_lms: int,
+    fps_h: Union[None, int] = None,
+    start_idx: Union[int, None] = None,
+) -> torch.Tensor:
+    """Selects landmarks using farthest-point sampling.
+
+    Same contract as the reference (``flooder/core.py:291-343``): returns ``points[idx]`` for the
+    FPS index sequence ``idx`` on the device and in the dtype of ``points``.  The sampling itself
+    is the persistent sm_100a kernel of ``csrc/fps.cu`` (exact FPS, float32).  ``fps_h`` (the
+    KD-tree height of the reference's bucket-FPS) is accepted for compatibility and has no
+    effect on the result.  ``start_idx=None`` picks the start index with ``np.random``.
+    """
+    del fps_h
+    if n_lms <= 0:
+        raise RuntimeError(f"Number of landmarks ({n_lms}) must be positive")
+    n_pts = len(points)
+    n_lms = min(int(n_lms), n_pts)
+    if start_idx is None:
+        start_idx = int(np.random.randint(n_pts))
+    dev_points = points
+    if points.device.type != "cuda":
+        if not torch.cuda.is_available():
+            _require_cuda(points, "points")
+        dev_points = points.cuda()
+    index_set = fps_indices(dev_points, n_lms, start_idx).to(points.device)
+    return points[index_set]
+
+
+# ----------------------------------------------------------------------------------------------
+# the filtration
+# ----------------------------------------------------------------------------------------------
+class PreparedCloud:
+    """Cell-sorted device copy of a point cloud (``flood_cloud_build_f32``)."""
+
+    def __init__(self, points: torch.Tensor, points_per_cell: int = 0):
+        _require_cuda(points, "points")
+        pts32 = points.detach().to(torch.float32).contiguous()
+        self.n, self.d = int(pts32.shape[0]), int(pts32.shape[1])
+        self.device = pts32.device
+        self.workspace = _native.ext().cloud_build(pts32, int(points_per_cell))
+
+
+def covering_values(
+    cloud: PreparedCloud,
+    simplex_vertices: torch.Tensor,
+    weights: torch.Tensor,
+    grid_mode: bool,
+    samples: Optional[torch.Tensor] = None,
+    return_details: bool = False,
+):
+    """Device part of one dimension pass: bounding balls -> covering-radius kernel -> face maxima.
+
+    Returns a float32 tensor ``(S, 2^K - 1)`` (grid mode; column ``m-1`` belongs to the face whose
+    vertex positions are the set bits of ``m``) or ``(S, 1)`` (random mode).
+    """
+    ext = _native.ext()
+    verts = simplex_vertices.to(torch.float32).contiguous()
+    w = weights.to(torch.float32).contiguous()
+    K = verts.shape[1]
+    centers, radii = ext.bounding_balls(verts)
+    min_d2, counts, evals = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples, centers, radii)
+    support = _support_masks(w) if grid_mode else None
+    values = ext.face_max(min_d2, support, K)
+    if return_details:
+        return values, dict(min_dist2=min_d2, cand_count=counts, evals=evals, centers=centers, radii=radii)
+    return values
+
+
+def _face_columns(K: int) -> List[Tuple[int, Tuple[int, ...]]]:
+    """(column, vertex positions) for every non-empty subset mask of K vertices."""
+    return [(m - 1, tuple(k for k in range(K) if m >> k & 1)) for m in range(1, 1 << K)]
+
+
+def _collect_faces(d_simplices: np.ndarray, values: np.ndarray, out: Dict[Tuple[int, ...], float]) -> None:
+    """Grid mode: spread the (S, 2^K-1) face values over the face keys.  A face shared by several
+    cells is computed once per coface from bit-identical sample points; the smallest value is
+    kept (it has seen the union of the cofaces' candidate balls)."""
+    K = d_simplices.shape[1]
+    by_size: Dict[int, List[Tuple[np.ndarray, np.ndarray]]] = {}
+    for col, pos in _face_columns(K):
+        by_size.setdefault(len(pos), []).append((d_simplices[:, list(pos)], values[:, col]))
+    for size, parts in by_size.items():
+        keys = np.concatenate([p[0] for p in parts], axis=0)
+        vals = np.concatenate([p[1] for p in parts], axis=0).astype(np.float64)
+        uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+        best = np.full(len(uniq), np.inf)
+        np.minimum.at(best, inv.reshape(-1), vals)
+        out.update(zip(map(tuple, uniq.tolist()), best.tolist()))
+
+
+def flood_complex(
+    points: torch.Tensor,
+    landmarks: Union[int, torch.Tensor],
+    max_dimension: Union[None, int] = None,
+    points_per_edge: Union[None, int] = 30,
+    num_rand: int = None,
+    batch_size: Union[None, int] = 64,
+    use_triton: Optional[bool] = None,
+    return_simplex_tree: bool = False,
+    fps_h: Union[None, int] = None,
+    start_idx: Union[int, None] = 0,
+) -> Union[dict, "SimplexTree"]:
+    """Constructs a Flood complex from witness points and landmarks.
+
+    Drop-in for the reference's ``flooder.flood_complex`` (``flooder/core.py:32-288``): same
+    arguments, same result (``{tuple(landmark indices): covering radius}`` for every simplex of the
+    Delaunay complex of the landmarks, or the simplex tree itself).  ``points`` and ``landmarks``
+    must live on a CUDA device.  ``batch_size``, ``use_triton`` and ``fps_h`` are accepted for
+    compatibility and ignored: there is no batching (the kernel never materialises a mask) and
+    no Triton path.  float64 inputs are accepted with the reference's ``RuntimeWarning`` and
+    computed in float32.
+
+    When ``torch.distributed`` is initialised with more than one rank, the simplex list is
+    sharded over the ranks (cloud replicated, see ``flooder_b200.distributed``) and the values
+    are all-gathered, so every rank returns the complete complex.
+    """
+    del batch_size, use_triton
+    if max_dimension is None:
+        max_dimension = points.shape[1]
+    if isinstance(landmarks, Integral):
+        landmarks = generate_landmarks(points, min(landmarks, points.shape[0]), fps_h, start_idx=start_idx)
+    if landmarks.device != points.device:
+        raise RuntimeError(f"landmarks.device ({landmarks.device}) != points.device ({points.device})")
+    if landmarks.dtype != points.dtype:
+        raise RuntimeError(f"landmarks.dtype ({landmarks.dtype}) != points.device ({points.dtype})")
+    device, dtype = points.device, points.dtype
+    if dtype not in _SUPPORTED_DTYPES:
+        raise TypeError(f"dtype ({dtype}) not supported")
+    if dtype is torch.float64:
+        warnings.warn(
+            "float64 inputs are evaluated in float32 by the sm_100a kernels",
+            RuntimeWarning,
+            stacklevel=2,
+        )
+    _require_cuda(points, "points")
+    torch.cuda.set_device(device)
+
+    lms32 = landmarks.detach().to(torch.float32)
+    stree = delaunay_simplex_tree(lms32.cpu().numpy())                     # host, as in the reference
+    simplices: List[List[Tuple[int, ...]]] = [[] for _ in range(max_dimension + 1)]
+    for simplex, _ in stree.get_simplices():
+        if len(simplex) <= max_dimension + 1:
+            simplices[len(simplex) - 1].append(tuple(simplex))
+
+    cloud = PreparedCloud(points)
+    shard = fdist.current_shard()
+    out_complex: Dict[Tuple[int, ...], float] = {}
+    for d in range(max_dimension + 1):
+        if num_rand is None and d < max_dimension:
+            continue
+        if len(simplices[d]) == 0:
+            continue
+        d_simplices_np = np.asarray(simplices[d], dtype=np.int64)
+        d_simplices = torch.as_tensor(d_simplices_np, device=device)
+        simplex_vertices = lms32[d_simplices]
+        if num_rand is None:
+            weights, _, _ = generate_grid(points_per_edge, max_dimension, device, torch.float32)
+        else:
+            weights = generate_uniform_weights(num_rand, d, device, torch.float32)
+        if shard is None:
+            values = covering_values(cloud, simplex_vertices, weights, grid_mode=num_rand is None)
+        else:
+            values = fdist.sharded_covering_values(
+                shard, simplex_vertices,
+                lambda v: covering_values(cloud, v, weights, grid_mode=num_rand is None),
+            )
+        values_np = values.cpu().numpy()
+        if num_rand is None:
+            _collect_faces(d_simplices_np, values_np, out_complex)
+        else:
+            out_complex.update(zip(simplices[d], values_np[:, 0].astype(np.float64).tolist()))
+
+    if isinstance(stree, SimplexTree):
+        stree.assign_many(list(out_complex.keys()), list(out_complex.values()))
+    else:  # pragma: no cover  (gudhi)
+        for simplex, value in out_complex.items():
+            stree.assign_filtration(simplex, value)
+    stree.make_filtration_non_decreasing()
+    if return_simplex_tree:
+        return stree
+    return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())

@@ -1,0 +1,123 @@
+// Shared declarations for libflood_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "flood_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define FLOOD_HOST_ONLY 1
+#endif
+
+namespace flood {
+
+// --------------------------------------------------------------------------------------
+// error reporting (thread-local message, see abi.cu)
+// --------------------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+
+#define FLOOD_CUDA_CHECK(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::flood::set_error(FLOOD_E_CUDA, "%s failed: %s (%s:%d)", #expr,         \
+                                      cudaGetErrorString(_e), __FILE__, __LINE__);          \
+    } while (0)
+
+#define FLOOD_LAUNCH_CHECK(name)                                                            \
+    do {                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess)                                                              \
+            return ::flood::set_error(FLOOD_E_CUDA, "launch of %s failed: %s", name,        \
+                                      cudaGetErrorString(_e));                              \
+    } while (0)
+
+int get_option(const char *name, int fallback);
+int device_sm_count();
+
+// --------------------------------------------------------------------------------------
+// prepared cloud: layout of the workspace filled by flood_cloud_build_f32
+// --------------------------------------------------------------------------------------
+// Cell grid over the first min(d,3) axes.  Lives in DEVICE memory (head of the cloud
+// workspace) so that no host synchronisation is needed between building and using it.
+struct GridParams {
+    float origin[3];   // lower corner of the cloud's bounding box
+    float inv_h;       // 1 / cell edge
+    float h;
+    int n[3];          // cells per axis (1 for unused axes)
+    int ncells;        // n[0]*n[1]*n[2]
+    int64_t npts;
+    int d;
+    int pad_;
+};
+
+constexpr int kMaxCellsLog2 = 21;
+constexpr int64_t kMaxCells = int64_t(1) << kMaxCellsLog2;
+
+__host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// floats per stored point record: 2 for d<=2, 4 for d<=4, 8 for d<=8
+__host__ __device__ constexpr int record_floats(int d) { return d <= 2 ? 2 : (d <= 4 ? 4 : 8); }
+
+struct CloudLayout {
+    int64_t off_grid;        // GridParams
+    int64_t off_bbox;        // 6 x uint32 (ordered-int encoded min/max)
+    int64_t off_cell_start;  // (max_cells + 1) x int32
+    int64_t off_cell_fill;   // max_cells x int32 (scratch)
+    int64_t off_cell_id;     // n x int32 (scratch)
+    int64_t off_points;      // n x record_floats(d) x float, cell-sorted
+    int64_t total;
+    int64_t max_cells;
+};
+
+__host__ __device__ inline int64_t cloud_max_cells(int64_t n) {
+    int64_t c = n / 4;
+    if (c < 64) c = 64;
+    if (c > kMaxCells) c = kMaxCells;
+    return c;
+}
+
+__host__ __device__ inline CloudLayout cloud_layout(int64_t n, int d) {
+    CloudLayout L;
+    L.max_cells = cloud_max_cells(n);
+    int64_t o = 0;
+    L.off_grid = o;        o = align_up(o + (int64_t)sizeof(GridParams), 256);
+    L.off_bbox = o;        o = align_up(o + 8 * 4, 256);
+    L.off_cell_start = o;  o = align_up(o + (L.max_cells + 1) * 4, 256);
+    L.off_cell_fill = o;   o = align_up(o + L.max_cells * 4, 256);
+    L.off_cell_id = o;     o = align_up(o + n * 4, 256);
+    L.off_points = o;      o = align_up(o + n * record_floats(d) * 4, 256);
+    L.total = o;
+    return L;
+}
+
+// cell coordinate of x along one axis (monotone in x); shared by the builder and the queries
+__device__ __forceinline__ float cell_coord(float x, float origin, float inv_h) {
+    return (x - origin) * inv_h;
+}
+__device__ __forceinline__ int cell_clamp(float g, int n) {
+    int i = (int)floorf(g);
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+// --------------------------------------------------------------------------------------
+// internal entry points (one per .cu file), wrapped by abi.cu
+// --------------------------------------------------------------------------------------
+int cloud_build(const float *pts, int64_t n, int d, int points_per_cell, void *ws, size_t ws_bytes,
+                cudaStream_t st);
+int bounding_balls(const float *verts, int64_t S, int K, int d, float *centers, float *radii,
+                   cudaStream_t st);
+size_t covering_workspace_bytes(int64_t S, int64_t R, int d);
+int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, int64_t S, int K,
+                    const float *weights, int64_t R, const float *samples, const float *centers,
+                    const float *radii, float *out_min_dist2, int64_t *out_cand_count,
+                    unsigned long long *out_evals, void *ws, size_t ws_bytes, cudaStream_t st);
+int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, float *out,
+             cudaStream_t st);
+size_t fps_workspace_bytes(int64_t n, int d, int64_t n_lms);
+int fps(const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx, int64_t *out_idx,
+        void *ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace flood

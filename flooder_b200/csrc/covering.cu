@@ -1,0 +1,567 @@
+// Covering-radius kernel family: for every simplex s and sample point x_sr on it,
+//     min_dist2[s, r] = min over the cloud points inside the simplex's bounding ball of |x_sr - p|^2.
+//
+// One fused persistent kernel replaces the reference's per-batch pipeline
+//     compute_mask (dense bool mask)  ->  torch.nonzero  ->  compute_filtration (gather + atomic_min)
+// (flooder/core.py:193-226, flooder/triton_kernels.py:12-45 and :99-158) and its
+// `weights @ vertices` matmul (core.py:188):
+//
+//   * work item  = (simplex, chunk of its candidate stream, block of its samples), pulled from a
+//     global atomic queue by persistent CTAs;
+//   * the candidate stream of a simplex is the concatenation of the cell-row runs its ball
+//     touches in the cell-sorted cloud (cloud.cu); a CTA enumerates the rows, prefix-sums the run
+//     lengths and gathers its window of the stream with a binary search per point;
+//   * every gathered point is tested against the ball (the reference predicate) and the
+//     survivors are compacted with warp ballots into a shared-memory tile of float4 records;
+//   * when the tile fills up, all warps sweep it: each thread keeps T sample points and their
+//     running minima in registers, tile records are broadcast LDS.128 reads, the distance is the
+//     direct difference form in FP32 FMA (D sub, 1 mul, D-1 fma, 1 min per pair);
+//   * the minima are merged into min_dist2 with an unsigned atomicMin (non-negative floats order
+//     like their bit patterns), because a simplex may be split over several chunks.
+//
+// The dense mask, the index lists and the (S, R, D) sample tensor never exist.
+#include "common.cuh"
+
+namespace flood {
+namespace {
+
+// candidate records per shared-memory tile (static shared memory is capped at 48 KB)
+__host__ __device__ constexpr int tile_cap(int d) { return d <= 4 ? 2048 : 1024; }
+constexpr int kUnroll = 4;       // candidates per inner-loop trip
+
+struct CoverParams {
+    const GridParams *gp;
+    const int *cell_start;
+    const void *points;
+    const float *verts;      // [S,K,D]
+    const float *weights;    // [R,K]
+    const float *samples;    // [S,R,D] or null
+    const float *centers;    // [S,D]
+    const float *radii;      // [S]
+    float *out;              // [S,R]
+    long long *cand_count;   // [S] or null
+    unsigned long long *evals;  // or null
+    int *tested;             // [S]     plan output
+    long long *item_base;    // [S+1]   exclusive prefix of chunks per simplex
+    unsigned long long *queue;
+    long long S, R;
+    int K;
+    int nsb;                 // sample blocks per simplex
+    int chunk;               // target tested points per chunk
+};
+
+// ---------------------------------------------------------------------------------------------
+// geometry of a ball in cell coordinates
+// ---------------------------------------------------------------------------------------------
+struct BallCells {
+    float gx, gy, gz, gr2;
+    int iy0, iz0, nyb, nrows;
+};
+
+__device__ __forceinline__ int clamp_cell(float v, int n) {
+    v = fminf(fmaxf(floorf(v), -1.0f), (float)n);
+    return (int)v;
+}
+
+__device__ __forceinline__ BallCells ball_cells(const float *c, float r, int d, const GridParams &gp) {
+    BallCells b;
+    b.gx = cell_coord(c[0], gp.origin[0], gp.inv_h);
+    b.gy = d > 1 ? cell_coord(c[1], gp.origin[1], gp.inv_h) : 0.5f;
+    b.gz = d > 2 ? cell_coord(c[2], gp.origin[2], gp.inv_h) : 0.5f;
+    // inflate: the cell mapping and the ball predicate are evaluated in float32
+    const float gr = r * gp.inv_h * (1.0f + 1e-5f) + 2e-3f;
+    b.gr2 = gr * gr;
+    int iy0 = max(0, clamp_cell(b.gy - gr, gp.n[1]));
+    int iy1 = min(gp.n[1] - 1, clamp_cell(b.gy + gr, gp.n[1]));
+    int iz0 = max(0, clamp_cell(b.gz - gr, gp.n[2]));
+    int iz1 = min(gp.n[2] - 1, clamp_cell(b.gz + gr, gp.n[2]));
+    b.iy0 = iy0;
+    b.iz0 = iz0;
+    b.nyb = max(0, iy1 - iy0 + 1);
+    b.nrows = b.nyb * max(0, iz1 - iz0 + 1);
+    return b;
+}
+
+// run [a, a+len) of cell-sorted points covered by the ball in cell row `row` (rows are numbered
+// in memory order: y fastest, then z)
+__device__ __forceinline__ void row_run(const BallCells &b, int row, const GridParams &gp,
+                                        const int *__restrict__ cell_start, int &a, int &len) {
+    const int iy = b.iy0 + row % b.nyb;
+    const int iz = b.iz0 + row / b.nyb;
+    const float dy = fmaxf(0.f, fmaxf((float)iy - b.gy, b.gy - (float)(iy + 1)));
+    const float dz = fmaxf(0.f, fmaxf((float)iz - b.gz, b.gz - (float)(iz + 1)));
+    const float rem = b.gr2 - dy * dy - dz * dz;
+    a = 0;
+    len = 0;
+    if (rem < 0.f) return;
+    const float half = sqrtf(rem);
+    const int ix0 = max(0, clamp_cell(b.gx - half, gp.n[0]));
+    const int ix1 = min(gp.n[0] - 1, clamp_cell(b.gx + half, gp.n[0]));
+    if (ix0 > ix1) return;
+    const int base = (iz * gp.n[1] + iy) * gp.n[0];
+    a = __ldg(cell_start + base + ix0);
+    len = __ldg(cell_start + base + ix1 + 1) - a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: tested[s] = length of the candidate stream of simplex s (one warp per simplex)
+// ---------------------------------------------------------------------------------------------
+__global__ void cover_plan_kernel(CoverParams P, int d) {
+    const GridParams gp = *P.gp;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= P.S) return;
+    float c[FLOOD_MAX_DIM];
+    for (int a = 0; a < d; ++a) c[a] = P.centers[warp * d + a];
+    const BallCells b = ball_cells(c, P.radii[warp], d, gp);
+    long long total = 0;
+    for (int row = lane; row < b.nrows; row += 32) {
+        int a, len;
+        row_run(b, row, gp, P.cell_start, a, len);
+        total += len;
+    }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) {
+        P.tested[warp] = (int)total;
+        // number of chunks, stored in place and scanned by cover_scan_kernel
+        P.item_base[warp] = (total + P.chunk - 1) / P.chunk;
+    }
+}
+
+// single-CTA exclusive scan (int64) of item_base[0..S) in place; item_base[S] = total
+__global__ void cover_scan_kernel(long long *v, long long S) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < S; base += blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const long long val = i < S ? v[i] : 0;
+        long long x = val;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = lane < nw ? warp_sums[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        if (i < S) v[i] = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + x - val;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_sums[nw - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v[S] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// point records
+// ---------------------------------------------------------------------------------------------
+template <int D> struct Rec;
+template <> struct Rec<2> { using type = float2; };
+template <> struct Rec<3> { using type = float4; };
+template <> struct Rec<4> { using type = float4; };
+template <int D> struct Rec { struct alignas(16) type { float4 a, b; }; };  // D = 5..8
+
+template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]);
+template <> __device__ __forceinline__ void rec_unpack<2>(const float2 &r, float (&p)[2]) { p[0] = r.x; p[1] = r.y; }
+template <> __device__ __forceinline__ void rec_unpack<3>(const float4 &r, float (&p)[3]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; }
+template <> __device__ __forceinline__ void rec_unpack<4>(const float4 &r, float (&p)[4]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; }
+template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]) {
+    const float q[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+    for (int a = 0; a < D; ++a) p[a] = q[a];
+}
+
+template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel();
+template <> __device__ __forceinline__ float2 rec_sentinel<2>() { return make_float2(INFINITY, INFINITY); }
+template <> __device__ __forceinline__ float4 rec_sentinel<3>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
+template <> __device__ __forceinline__ float4 rec_sentinel<4>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
+template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel() {
+    typename Rec<D>::type r;
+    r.a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    r.b = r.a;
+    return r;
+}
+
+// squared distance, direct difference form: (x0-p0)^2 rounded, then FMA accumulation
+template <int D>
+__device__ __forceinline__ float dist2(const float (&x)[D], const float (&p)[D]) {
+    float t = x[0] - p[0];
+    float acc = t * t;
+#pragma unroll
+    for (int a = 1; a < D; ++a) {
+        t = x[a] - p[a];
+        acc = fmaf(t, t, acc);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in `total`
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();  // protect warp_sums from the previous use
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    int prefix = 0, tot = 0;
+    // nw <= 32: every thread folds the warp totals it needs (broadcast LDS, no third barrier)
+    for (int w = 0; w < nw; ++w) {
+        int s = warp_sums[w];
+        if (w < warp) prefix += s;
+        tot += s;
+    }
+    total = tot;
+    return prefix + x - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent evaluation kernel
+// ---------------------------------------------------------------------------------------------
+template <int D, int T, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
+    using RecT = typename Rec<D>::type;
+    constexpr int NTMAX = MAXW * 32;
+
+    constexpr int kTileCap = tile_cap(D);
+    __shared__ RecT tile[kTileCap + kUnroll];
+    __shared__ int run_start[NTMAX];
+    __shared__ int run_pos[NTMAX + 1];
+    __shared__ int warp_sums[32];
+    __shared__ int s_fill;
+    __shared__ long long s_item[3];  // simplex, chunk, sample block (-1 = queue drained)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x;
+    const GridParams gp = *P.gp;
+    const RecT *__restrict__ points = reinterpret_cast<const RecT *>(P.points);
+    const long long total_chunks = P.item_base[P.S];
+    const unsigned long long total_items = (unsigned long long)total_chunks * (unsigned)P.nsb;
+    const int SB = NT * T;
+
+    if (tid == 0) s_fill = 0;
+
+    for (;;) {
+        // ---- fetch a work item ---------------------------------------------------------------
+        __syncthreads();  // previous item fully retired (s_item, tile, run arrays reusable)
+        if (tid == 0) {
+            const unsigned long long g = atomicAdd(P.queue, 1ull);
+            if (g >= total_items) {
+                s_item[0] = -1;
+            } else {
+                const long long gi = (long long)(g / (unsigned)P.nsb);
+                long long lo = 0, hi = P.S;  // last s with item_base[s] <= gi
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (P.item_base[mid] <= gi) lo = mid; else hi = mid;
+                }
+                s_item[0] = lo;
+                s_item[1] = gi - P.item_base[lo];
+                s_item[2] = (long long)(g % (unsigned)P.nsb);
+            }
+        }
+        __syncthreads();
+        const long long s = s_item[0];
+        if (s < 0) break;
+        const long long chunk_j = s_item[1];
+        const int sb = (int)s_item[2];
+
+        // ---- simplex constants ---------------------------------------------------------------
+        float c[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) c[a] = __ldg(P.centers + s * D + a);
+        const float rad = __ldg(P.radii + s);
+        const float r2 = rad * rad;
+        const BallCells bc = ball_cells(c, rad, D, gp);
+        const long long tested = P.tested[s];
+        const long long nch = P.item_base[s + 1] - P.item_base[s];
+        const int win_lo = (int)(chunk_j * tested / nch);
+        const int win_hi = (int)((chunk_j + 1) * tested / nch);
+
+        // ---- this thread's sample points -----------------------------------------------------
+        float x[T][D], m[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const long long r = (long long)sb * SB + warp * (32 * T) + t * 32 + lane;
+            m[t] = INFINITY;
+            if (r < P.R) {
+                if (P.samples) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) x[t][a] = __ldg(P.samples + (s * P.R + r) * D + a);
+                } else {
+                    // x = sum_k w[r,k] * v[s,k,:], FMA chain over k ascending (== the reference's
+                    // float32 matmul, core.py:188)
+                    const float *w = P.weights + r * P.K;
+                    const float *v = P.verts + s * P.K * D;
+                    const float w0 = __ldg(w);
+#pragma unroll
+                    for (int a = 0; a < D; ++a) x[t][a] = __fmul_rn(w0, __ldg(v + a));
+                    for (int k = 1; k < P.K; ++k) {
+                        const float wk = __ldg(w + k);
+#pragma unroll
+                        for (int a = 0; a < D; ++a) x[t][a] = fmaf(wk, __ldg(v + k * D + a), x[t][a]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < D; ++a) x[t][a] = c[a];
+            }
+        }
+
+        // sweep of the shared tile by all warps: the hot loop
+        auto sweep = [&](int n) {
+            const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
+            if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
+            __syncthreads();
+#pragma unroll 1
+            for (int j = 0; j < npad; j += kUnroll) {
+                float p[kUnroll][D];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) m[t] = fminf(m[t], dist2<D>(x[t], p[u]));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_fill = 0;
+        };
+
+        // ---- stream the candidate window -----------------------------------------------------
+        int fill = 0;
+        long long accepted = 0;
+        int carry = 0;  // stream offset of the current row batch
+        for (int rb = 0; rb < bc.nrows; rb += NT) {
+            if (carry >= win_hi) break;
+            const int row = rb + tid;
+            int a = 0, len = 0;
+            if (row < bc.nrows) row_run(bc, row, gp, P.cell_start, a, len);
+            int batch_total;
+            const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
+            const int batch_lo = carry;
+            carry += batch_total;
+            if (carry <= win_lo) continue;
+            (void)batch_lo;
+            // clip the run to this chunk's window of the stream
+            const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
+            const int len2 = max(0, s1 - s0);
+            int total2;
+            const int pos2 = block_exclusive_scan(len2, warp_sums, total2);
+            run_start[tid] = a + (s0 - off);
+            run_pos[tid] = pos2;
+            if (tid == 0) run_pos[NT] = total2;
+            __syncthreads();
+
+            for (int base = 0; base < total2; base += NT) {
+                if (fill + NT > kTileCap) {
+                    accepted += fill;
+                    sweep(fill);
+                    __syncthreads();
+                    fill = 0;
+                }
+                const int q = base + tid;
+                bool pass = false;
+                RecT rec;
+                if (q < total2) {
+                    // last run with run_pos <= q
+                    int lo = 0, hi = NT;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (run_pos[mid] <= q) lo = mid; else hi = mid;
+                    }
+                    rec = points[run_start[lo] + (q - run_pos[lo])];
+                    float p[D];
+                    rec_unpack<D>(rec, p);
+                    // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
+                    float t = p[0] - c[0];
+                    float acc = t * t;
+#pragma unroll
+                    for (int a2 = 1; a2 < D; ++a2) {
+                        t = p[a2] - c[a2];
+                        acc = fmaf(t, t, acc);
+                    }
+                    pass = acc <= r2;
+                }
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                int wbase = 0;
+                if (lane == 0 && ballot) wbase = atomicAdd(&s_fill, __popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (pass) tile[wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
+                __syncthreads();
+                fill = s_fill;
+            }
+        }
+        if (fill > 0) {
+            accepted += fill;
+            sweep(fill);
+        }
+
+        // ---- merge -----------------------------------------------------------------------------
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const long long r = (long long)sb * SB + warp * (32 * T) + t * 32 + lane;
+            if (r < P.R && m[t] < INFINITY)
+                atomicMin(reinterpret_cast<unsigned *>(P.out + s * P.R + r), __float_as_uint(m[t]));
+        }
+        if (tid == 0 && sb == 0 && accepted > 0) {
+            if (P.cand_count) atomicAdd(reinterpret_cast<unsigned long long *>(P.cand_count + s),
+                                        (unsigned long long)accepted);
+            if (P.evals) atomicAdd(P.evals, (unsigned long long)accepted * (unsigned long long)P.R);
+        }
+    }
+}
+
+__global__ void fill_inf_kernel(float *p, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        p[i] = INFINITY;
+}
+
+struct CoverLayout {
+    int64_t off_tested, off_item_base, off_queue, total;
+};
+
+CoverLayout cover_layout(int64_t S) {
+    CoverLayout L;
+    int64_t o = 0;
+    L.off_queue = o;      o = align_up(o + 64, 256);
+    L.off_tested = o;     o = align_up(o + S * 4, 256);
+    L.off_item_base = o;  o = align_up(o + (S + 1) * 8, 256);
+    L.total = o;
+    return L;
+}
+
+template <int D, int T, int MAXW, int MINB>
+int launch_eval(const CoverParams &P, int nwarps, cudaStream_t st) {
+    auto kern = cover_eval_kernel<D, T, MAXW, MINB>;
+    int per_sm = 0;
+    FLOOD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, 0));
+    if (per_sm < 1) return set_error(FLOOD_E_CUDA, "cover_eval_kernel does not fit on an SM");
+    const int cap = get_option("ctas_per_sm", 0);
+    if (cap > 0 && per_sm > cap) per_sm = cap;
+    const int grid = device_sm_count() * per_sm;
+    kern<<<grid, nwarps * 32, 0, st>>>(P);
+    FLOOD_LAUNCH_CHECK("cover_eval_kernel");
+    return FLOOD_OK;
+}
+
+template <int D>
+int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
+    // T = samples per thread, MAXW = warps per CTA.  Wide CTAs (20 warps, one per SM) cover the
+    // reference default R = 4960 (3-D, 30 points per edge) in one sample block.
+    const int mode = get_option("eval_mode", 0);
+    if (mode == 1) {  // 2 CTAs per SM, 10 warps each
+        constexpr int T = 8, MAXW = 10;
+        int nwarps = (int)((R + 32 * T - 1) / (32 * T));
+        if (nwarps > MAXW) nwarps = MAXW;
+        P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
+        return launch_eval<D, T, MAXW, 2>(P, nwarps, st);
+    }
+    if (R <= 32 * 4 * 8) {  // small sample sets: fewer samples per thread, more warps
+        constexpr int T = 4, MAXW = 8;
+        int nwarps = (int)((R + 32 * T - 1) / (32 * T));
+        if (nwarps > MAXW) nwarps = MAXW;
+        P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
+        return launch_eval<D, T, MAXW, 4>(P, nwarps, st);
+    }
+    constexpr int T = 8, MAXW = 20;
+    int nwarps = (int)((R + 32 * T - 1) / (32 * T));
+    if (nwarps > MAXW) nwarps = MAXW;
+    P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
+    return launch_eval<D, T, MAXW, 1>(P, nwarps, st);
+}
+
+}  // namespace
+
+size_t covering_workspace_bytes(int64_t S, int64_t R, int d) {
+    (void)R; (void)d;
+    return (size_t)cover_layout(S < 1 ? 1 : S).total;
+}
+
+int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, int64_t S, int K,
+                    const float *weights, int64_t R, const float *samples, const float *centers,
+                    const float *radii, float *out_min_dist2, int64_t *out_cand_count,
+                    unsigned long long *out_evals, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (S == 0) return FLOOD_OK;
+    if (!cloud_ws || !centers || !radii || !out_min_dist2 || !ws || S < 0 || R < 1 || n < 1 ||
+        d < 2 || d > FLOOD_MAX_DIM || K < 1 || K > FLOOD_MAX_SIMPLEX_VERTS)
+        return set_error(FLOOD_E_INVALID, "covering_radius: bad arguments (S=%lld R=%lld n=%lld d=%d K=%d)",
+                         (long long)S, (long long)R, (long long)n, d, K);
+    if (!samples && (!verts || !weights))
+        return set_error(FLOOD_E_INVALID, "covering_radius: need either samples or (verts, weights)");
+    const CoverLayout L = cover_layout(S);
+    if ((int64_t)ws_bytes < L.total)
+        return set_error(FLOOD_E_WORKSPACE, "covering_radius: workspace %zu < %lld bytes", ws_bytes,
+                         (long long)L.total);
+    const CloudLayout C = cloud_layout(n, d);
+    const char *cbase = static_cast<const char *>(cloud_ws);
+    char *wbase = static_cast<char *>(ws);
+
+    CoverParams P;
+    P.gp = reinterpret_cast<const GridParams *>(cbase + C.off_grid);
+    P.cell_start = reinterpret_cast<const int *>(cbase + C.off_cell_start);
+    P.points = cbase + C.off_points;
+    P.verts = verts;
+    P.weights = weights;
+    P.samples = samples;
+    P.centers = centers;
+    P.radii = radii;
+    P.out = out_min_dist2;
+    P.cand_count = reinterpret_cast<long long *>(out_cand_count);
+    P.evals = out_evals;
+    P.tested = reinterpret_cast<int *>(wbase + L.off_tested);
+    P.item_base = reinterpret_cast<long long *>(wbase + L.off_item_base);
+    P.queue = reinterpret_cast<unsigned long long *>(wbase + L.off_queue);
+    P.S = S;
+    P.R = R;
+    P.K = K;
+    P.nsb = 1;
+    P.chunk = get_option("chunk", 8192);
+    if (P.chunk < 256) P.chunk = 256;
+
+    FLOOD_CUDA_CHECK(cudaMemsetAsync(P.queue, 0, 64, st));
+    if (out_cand_count) FLOOD_CUDA_CHECK(cudaMemsetAsync(out_cand_count, 0, (size_t)S * 8, st));
+    {
+        const long long total = S * R;
+        int blocks = (int)((total + 1023) / 1024);
+        const int cap = device_sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        fill_inf_kernel<<<blocks, 256, 0, st>>>(out_min_dist2, total);
+    }
+    {
+        const int threads = 128;  // 4 simplices per CTA
+        const long long blocks = (S * 32 + threads - 1) / threads;
+        cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
+        cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base, S);
+    }
+    FLOOD_LAUNCH_CHECK("cover plan kernels");
+    switch (d) {
+        case 2: return dispatch_eval<2>(P, R, st);
+        case 3: return dispatch_eval<3>(P, R, st);
+        case 4: return dispatch_eval<4>(P, R, st);
+        case 5: return dispatch_eval<5>(P, R, st);
+        case 6: return dispatch_eval<6>(P, R, st);
+        case 7: return dispatch_eval<7>(P, R, st);
+        case 8: return dispatch_eval<8>(P, R, st);
+    }
+    return set_error(FLOOD_E_UNSUPPORTED, "covering_radius: d=%d", d);
+}
+
+}  // namespace flood

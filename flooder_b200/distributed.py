@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the covering-radius pass (one process per GPU, torch.distributed).
+
+The reference is single-process / single-GPU, so this is new: the value
+of a simplex depends only on its own vertices and on the point cloud, hence the simplex list
+shards with no data-path exchange.  Every rank holds the whole cloud on its own GPU, evaluates
+its share of the simplices, and the per-simplex values (S x (2^K - 1) floats, a few hundred KB)
+are all-gathered -- NCCL over NVLink when the process group is NCCL, gloo in the CPU tests.
+Landmark FPS and the host Delaunay step are replicated (deterministic), not sharded.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import torch
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    group: Optional[object] = None
+
+
+def current_shard() -> Optional[Shard]:
+    """The active shard when torch.distributed is initialised with >1 ranks (and sharding is not
+    disabled with FLOODER_B200_NO_SHARD=1), else None."""
+    if os.environ.get("FLOODER_B200_NO_SHARD", "0") == "1":
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size()
+    if world <= 1:
+        return None
+    return Shard(rank=dist.get_rank(), world=world)
+
+
+def partition(cost: torch.Tensor, world: int) -> List[torch.Tensor]:
+    """Deal simplices to ranks round-robin in order of decreasing cost proxy.
+
+    The heavy tail (a few simplices whose ball swallows most of the cloud) is spread first, and
+    every rank receives the same cost distribution.  Deterministic: ties are broken by index.
+    Returns one int64 index tensor per rank (on ``cost.device``)."""
+    order = torch.argsort(cost, descending=True, stable=True)
+    return [order[r::world].contiguous() for r in range(world)]
+
+
+def cost_proxy(simplex_vertices: torch.Tensor) -> torch.Tensor:
+    """Longest edge of each simplex (the bounding-ball radius is proportional to it)."""
+    v = simplex_vertices
+    diff = v[:, :, None, :] - v[:, None, :, :]
+    return diff.square().sum(dim=3).flatten(1).amax(dim=1)
+
+
+def gather_rows(local: torch.Tensor, parts: List[torch.Tensor], shard: Shard) -> torch.Tensor:
+    """All-gather per-rank row blocks (``local`` holds the rows ``parts[rank]``) into the full
+    (S, W) tensor on every rank."""
+    import torch.distributed as dist
+
+    world = shard.world
+    width = local.shape[1]
+    rows_max = max(int(p.numel()) for p in parts)
+    padded = torch.zeros((rows_max, width), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=shard.group)
+    total = sum(int(p.numel()) for p in parts)
+    full = torch.empty((total, width), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        full[parts[r].to(local.device)] = gathered[r][: parts[r].numel()]
+    return full
+
+
+def sharded_covering_values(
+    shard: Shard,
+    simplex_vertices: torch.Tensor,
+    compute: Callable[[torch.Tensor], torch.Tensor],
+) -> torch.Tensor:
+    """Evaluate ``compute`` on this rank's share of the simplices and all-gather the rows."""
+    parts = partition(cost_proxy(simplex_vertices), shard.world)
+    mine = parts[shard.rank]
+    local = compute(simplex_vertices[mine].contiguous())
+    return gather_rows(local, parts, shard)

@@ -1,0 +1,165 @@
+"""Host-side complex container and Delaunay step.
+
+The reference keeps both inside gudhi (``gudhi.DelaunayComplex(landmarks).create_simplex_tree()``,
+``flooder/core.py:130-132``; ``assign_filtration`` / ``make_filtration_non_decreasing`` /
+``get_simplices``, ``:278-288``).  When gudhi is importable it is used exactly like that and
+``flood_complex(..., return_simplex_tree=True)`` returns a real ``gudhi.SimplexTree``.  The build
+image has no gudhi, so this module also provides a small array-oriented ``SimplexTree`` with the
+same method names, and a Qhull-based triangulation (``scipy.spatial.Delaunay``), which produces
+the same simplex sets as gudhi/CGAL on every fixture the reference ships (tests/golden).
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+try:  # pragma: no cover - not available in the build image
+    import gudhi as _gudhi
+
+    HAS_GUDHI = hasattr(_gudhi, "DelaunayComplex")
+except Exception:  # noqa: BLE001
+    _gudhi = None
+    HAS_GUDHI = False
+
+
+def delaunay_cells(landmarks: np.ndarray) -> np.ndarray:
+    """Top-dimensional Delaunay cells as ascending vertex index rows, shape (S, D+1)."""
+    from scipy.spatial import Delaunay
+
+    pts = np.asarray(landmarks, dtype=np.float64)
+    n, d = pts.shape
+    if n <= d:  # not enough points for a full-dimensional cell
+        return np.arange(n, dtype=np.int64)[None, :]
+    cells = Delaunay(pts).simplices.astype(np.int64)
+    cells.sort(axis=1)
+    return cells
+
+
+def faces_of_cells(cells: np.ndarray, k: int) -> np.ndarray:
+    """Unique (k-1)-dimensional faces (k vertices) of the given cells, rows ascending."""
+    cells = np.asarray(cells, dtype=np.int64)
+    width = cells.shape[1]
+    if k == width:
+        return np.unique(cells, axis=0)
+    cols = np.array(list(itertools.combinations(range(width), k)), dtype=np.int64)
+    faces = cells[:, cols].reshape(-1, k)
+    return np.unique(faces, axis=0)
+
+
+class SimplexTree:
+    """Filtered simplicial complex keyed by ascending vertex tuples.
+
+    Mirrors the subset of ``gudhi.SimplexTree`` that the reference and its tests touch.
+    Unassigned simplices carry NaN (what gudhi's DelaunayComplex hands out with
+    ``filtration=None``).
+    """
+
+    def __init__(self) -> None:
+        self._f: Dict[Tuple[int, ...], float] = {}
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def from_cells(cls, cells: np.ndarray) -> "SimplexTree":
+        st = cls()
+        nan = float("nan")
+        width = np.asarray(cells).shape[1]
+        for k in range(1, width + 1):
+            st._f.update(dict.fromkeys(map(tuple, faces_of_cells(cells, k).tolist()), nan))
+        return st
+
+    def insert(self, simplex: Iterable[int], filtration: float = 0.0) -> bool:
+        key = tuple(sorted(int(v) for v in simplex))
+        filtration = float(filtration)
+        changed = False
+        for k in range(1, len(key) + 1):
+            for face in itertools.combinations(key, k):
+                old = self._f.get(face)
+                if old is None or filtration < old:
+                    self._f[face] = filtration
+                    changed = True
+        return changed
+
+    # ---- queries ------------------------------------------------------------------------
+    def num_simplices(self) -> int:
+        return len(self._f)
+
+    def num_vertices(self) -> int:
+        return sum(1 for k in self._f if len(k) == 1)
+
+    def dimension(self) -> int:
+        return max((len(k) for k in self._f), default=0) - 1
+
+    def find(self, simplex: Iterable[int]) -> bool:
+        return tuple(sorted(simplex)) in self._f
+
+    def filtration(self, simplex: Iterable[int]) -> float:
+        return self._f[tuple(sorted(simplex))]
+
+    def get_simplices(self) -> Iterator[Tuple[List[int], float]]:
+        for key in sorted(self._f, key=lambda k: (len(k), k)):
+            yield list(key), self._f[key]
+
+    def get_skeleton(self, dimension: int) -> Iterator[Tuple[List[int], float]]:
+        for key, val in self.get_simplices():
+            if len(key) <= dimension + 1:
+                yield key, val
+
+    def get_filtration(self) -> Iterator[Tuple[List[int], float]]:
+        def order(k):
+            v = self._f[k]
+            return (math.inf if math.isnan(v) else v, len(k), k)
+
+        for key in sorted(self._f, key=order):
+            yield list(key), self._f[key]
+
+    def get_boundaries(self, simplex: Iterable[int]) -> Iterator[Tuple[List[int], float]]:
+        key = tuple(sorted(simplex))
+        if len(key) > 1:
+            for i in range(len(key)):
+                face = key[:i] + key[i + 1:]
+                yield list(face), self._f[face]
+
+    # ---- mutation -----------------------------------------------------------------------
+    def assign_filtration(self, simplex: Iterable[int], filtration: float) -> None:
+        key = tuple(sorted(simplex))
+        if key not in self._f:
+            raise KeyError(f"simplex {key} is not in the complex")
+        self._f[key] = float(filtration)
+
+    def assign_many(self, simplices: Sequence[Tuple[int, ...]], values: Sequence[float]) -> None:
+        """Bulk ``assign_filtration`` for keys that are already ascending tuples."""
+        self._f.update(zip(simplices, values))
+
+    def make_filtration_non_decreasing(self) -> bool:
+        """Every simplex is raised to the largest value among its facets, by increasing
+        dimension; NaN (unassigned) counts as minus infinity."""
+        f = self._f
+        changed = False
+        for key in sorted(f, key=len):
+            n = len(key)
+            if n == 1:
+                continue
+            best = -math.inf
+            for i in range(n):
+                v = f[key[:i] + key[i + 1:]]
+                if v > best:  # False for NaN
+                    best = v
+            cur = f[key]
+            if best > -math.inf and not cur >= best:  # cur < best or cur is NaN
+                f[key] = best
+                changed = True
+        return changed
+
+    def to_dict(self) -> Dict[Tuple[int, ...], float]:
+        return {tuple(s): v for s, v in self.get_simplices()}
+
+
+def delaunay_simplex_tree(landmarks: np.ndarray):
+    """(tree, cells): gudhi objects when gudhi is installed, the stand-ins otherwise."""
+    if HAS_GUDHI:  # pragma: no cover
+        tree = _gudhi.DelaunayComplex(np.asarray(landmarks)).create_simplex_tree()
+        return tree
+    return SimplexTree.from_cells(delaunay_cells(landmarks))

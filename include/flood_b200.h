@@ -1,0 +1,122 @@
+/* flood_b200.h -- C ABI of libflood_b200.so: the B200-native (sm_100a) Flood-complex hot path.
+ *
+ * The reference (plus-rkwitt/flooder) has no FFI layer; its seams for this path are Python
+ * call sites.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root):
+ *
+ *   flood_fps_f32                 fpsample.bucket_fps_kdline_sampling(...)      flooder/core.py:337-342
+ *   flood_cloud_build_f32         sort of the cloud + slab search column         flooder/core.py:140-144, 201-208
+ *   flood_bounding_balls_f32      simplex centres / radii                        flooder/core.py:156-172
+ *   flood_covering_radius_f32     compute_mask + torch.nonzero + compute_filtration
+ *                                 (+ the weights @ vertices product)             flooder/core.py:188, 210-226
+ *                                                                                flooder/triton_kernels.py:48-96, 161-223
+ *   flood_face_max_f32            per-face / per-simplex maxima                  flooder/core.py:251-257, 270
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it is marked "host";
+ *     the library never allocates or frees device memory: scratch space is passed in as a
+ *     workspace whose size the matching *_workspace_bytes() function reports;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and the calls return without synchronising, except where stated;
+ *   - return value 0 = success, negative = error (FLOOD_E_*); a human-readable message for
+ *     the calling thread's last error is returned by flood_last_error();
+ *   - no exceptions cross the boundary; the functions are re-entrant per (device, stream)
+ *     as long as the workspaces are distinct.
+ */
+#ifndef FLOOD_B200_H
+#define FLOOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOOD_ABI_VERSION 1
+
+#define FLOOD_OK 0
+#define FLOOD_E_INVALID (-1)   /* bad argument (null pointer, unsupported dimension, ...) */
+#define FLOOD_E_WORKSPACE (-2) /* workspace too small */
+#define FLOOD_E_CUDA (-3)      /* a CUDA runtime call or launch failed */
+#define FLOOD_E_UNSUPPORTED (-4)
+
+#define FLOOD_MAX_DIM 8          /* ambient dimension D: 1..8 */
+#define FLOOD_MAX_SIMPLEX_VERTS 9 /* K = d+1 <= D+1 */
+
+int flood_abi_version(void);
+const char *flood_last_error(void);
+
+/* Number of SMs / clock of the current device (used by the benchmark's roofline). */
+int flood_device_info(int *sm_count, int *sm_clock_khz);
+
+/* ---------------------------------------------------------------------------------------
+ * Farthest-point sampling (exact).  idx[0] = start_idx,
+ *   idx[k+1] = argmax_i min_{j<=k} |p_i - p_idx[j]|^2      (first maximum wins)
+ * float32, squared distance summed in coordinate order WITHOUT fused multiply-add, i.e. the
+ * arithmetic of a scalar CPU implementation, so that indices are bit-exact.
+ * pts: [n, d] row-major.  out_idx: [n_lms] int64.  Persistent cooperative kernel.
+ * ------------------------------------------------------------------------------------- */
+size_t flood_fps_workspace_bytes(int64_t n, int d, int64_t n_lms);
+int flood_fps_f32(const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx,
+                  int64_t *out_idx, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Cloud preparation: bins the cloud into a uniform cell grid over its first min(d,3) axes and
+ * stores it cell-sorted as padded float4 records, so that a ball maps to a few contiguous
+ * runs.  The prepared cloud lives entirely inside `workspace`; the same (pointer, n, d) triple
+ * is handed to flood_covering_radius_f32.  points_per_cell <= 0 selects the default.
+ * ------------------------------------------------------------------------------------- */
+size_t flood_cloud_workspace_bytes(int64_t n, int d);
+int flood_cloud_build_f32(const float *pts, int64_t n, int d, int points_per_cell,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Bounding balls of simplices, the reference's candidate rule:
+ *   centre = midpoint of the longest edge (first maximum of the flattened KxK distance matrix),
+ *   radius = max_k |v_k - centre| * (K > 2 ? 1.42 : 1.01) + 1e-3.
+ * verts: [S, K, d].  centers: [S, d].  radii: [S].
+ * ------------------------------------------------------------------------------------- */
+int flood_bounding_balls_f32(const float *verts, int64_t S, int K, int d, float *centers,
+                             float *radii, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Covering radius samples.  For every simplex s and sample r
+ *     out_min_dist2[s, r] = min_{p in cloud, sum_i (p_i - c_s,i)^2 <= r_s^2} |x_sr - p|^2
+ * with x_sr = sum_k weights[r, k] * verts[s, k, :] (fused multiply-add chain over k
+ * ascending; bit-identical to the reference's float32 matmul) or, when `samples` is not
+ * NULL, x_sr = samples[s, r, :].  Distances are direct differences in float32
+ * ((x-p)^2 accumulated with FMA), +inf when the ball holds no cloud point.
+ *
+ *   cloud_workspace   result of flood_cloud_build_f32 for (n, d)
+ *   verts             [S, K, d]       weights  [R, K]        samples  [S, R, d] or NULL
+ *   centers, radii    [S, d], [S]     (flood_bounding_balls_f32 or caller-supplied)
+ *   out_min_dist2     [S, R] float32  squared distances
+ *   out_cand_count    [S] int64 or NULL: number of cloud points inside ball s
+ *   out_evals         host-invisible device counter (1 x uint64) or NULL: sum_s R * cand_count[s],
+ *                     the algorithmic work count E of the call
+ * ------------------------------------------------------------------------------------- */
+size_t flood_covering_workspace_bytes(int64_t S, int64_t R, int d);
+int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, const float *verts,
+                              int64_t S, int K, const float *weights, int64_t R,
+                              const float *samples, const float *centers, const float *radii,
+                              float *out_min_dist2, int64_t *out_cand_count,
+                              unsigned long long *out_evals, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Face maxima.  support: [R] int32 bit masks (bit k set <=> weights[r, k] != 0) or NULL.
+ *   support != NULL (grid mode):  out[s, m-1] = sqrt(max_{r : support[r] subset of m} min_dist2[s, r])
+ *                                 for every non-empty vertex subset m in 1 .. 2^K - 1
+ *   support == NULL (random mode): out[s] = sqrt(max_r min_dist2[s, r])
+ * ------------------------------------------------------------------------------------- */
+int flood_face_max_f32(const float *min_dist2, int64_t S, int64_t R, const int32_t *support,
+                       int K, float *out, void *stream);
+
+/* Tuning knobs for experiments (process-wide; return the previous value).  */
+int flood_set_option(const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOOD_B200_H */

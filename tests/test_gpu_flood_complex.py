@@ -1,0 +1,139 @@
+"""GPU parity of the public API against the CPU oracle and the golden fixtures.
+
+Tolerance: the oracle measures exact nearest-neighbour distances in float64 on the same
+float32 sample points (the CUDA kernel builds them with the same FMA chain); the kernel's
+direct-difference float32 distance then carries a few ulps -> rtol 1e-5 as north_star states,
+plus atol 1e-7 for values that are exactly 0 in one arithmetic and ~1e-8 in the other.
+"""
+import numpy as np
+import pytest
+import torch
+
+import flooder_b200 as fb
+from oracle import flood_oracle
+from tests.helpers import (REF_CASES, assert_close_dict, golden_dict, golden_kwargs, load_golden,
+                           seed_all)
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-7
+DEV = torch.device("cuda")
+
+
+@pytest.mark.parametrize("case", REF_CASES)
+def test_golden_reference_runs(case):
+    """flood_complex == what the reference itself returned for these inputs (tests/golden)."""
+    g = load_golden("ref_" + case)
+    pts = torch.as_tensor(g["points"]).to(DEV)
+    lms = torch.as_tensor(g["landmarks"]).to(DEV)
+    seed_all()
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        got = fb.flood_complex(pts, lms, **golden_kwargs(g))
+    # f64 fixture: the kernels compute in float32 -> the reference's own f32/f64 bound (3e-6)
+    atol = 3e-6 if case.endswith("f64") else ATOL
+    assert_close_dict(got, golden_dict(g), rtol=RTOL, atol=atol, what=case)
+
+
+def test_shipped_animation_csv():
+    g = load_golden("shipped_animation")
+    got = fb.flood_complex(torch.as_tensor(g["points"]).to(DEV), torch.as_tensor(g["landmarks"]).to(DEV),
+                           points_per_edge=int(g["points_per_edge"]))
+    for a, b, f in g["edges"]:
+        assert abs(got[(int(a), int(b))] - f) <= RTOL * f + 2e-8
+    for a, b, c, f in g["triangles"]:
+        assert abs(got[(int(a), int(b), int(c))] - f) <= RTOL * f + 2e-8
+
+
+@pytest.mark.parametrize("num_witnesses", [1000, 10_000])
+@pytest.mark.parametrize("num_landmarks", [20, 701, 2000])
+@pytest.mark.parametrize("use_rand", [True, False])
+def test_kdtree_vs_gpu(num_witnesses, num_landmarks, use_rand):
+    """Mirror of the reference's test_kdtree_vs_triton (tests/test_flooder.py:119-157) with the
+    tighter tolerance; includes n_landmarks > n_points (clamping)."""
+    kwargs = {"num_rand": 512, "points_per_edge": None} if use_rand else {"num_rand": None, "points_per_edge": 20}
+    seed_all()
+    X = fb.generate_noisy_torus_points_3d(num_witnesses).to(DEV)
+    L = fb.generate_landmarks(X, num_landmarks, start_idx=0)
+    assert L.shape == (min(num_landmarks, num_witnesses), 3) and L.device == X.device
+    seed_all()
+    got = fb.flood_complex(X, L, **kwargs)
+    seed_all()
+    want = flood_oracle.flood_complex(X.cpu().numpy(), L.cpu().numpy(), **kwargs)
+    assert_close_dict(got, want, rtol=RTOL, atol=ATOL)
+
+
+def test_landmarks_from_int_and_fps_parity():
+    seed_all()
+    X = fb.generate_noisy_torus_points_3d(20_000).to(DEV)
+    got = fb.flood_complex(X, 150, points_per_edge=10)
+    lms = flood_oracle.generate_landmarks(X.cpu().numpy(), 150, 0)
+    np.testing.assert_array_equal(fb.generate_landmarks(X, 150, start_idx=0).cpu().numpy(), lms)
+    want = flood_oracle.flood_complex(X.cpu().numpy(), lms, points_per_edge=10)
+    assert_close_dict(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("num_witnesses", [1000, 10_000])
+@pytest.mark.parametrize("num_landmarks", [20, 1000])
+@pytest.mark.parametrize("return_simplex_tree", [True, False])
+def test_filtration_condition(num_witnesses, num_landmarks, return_simplex_tree):
+    """Reference tests/test_flooder.py:160-211: the result is a filtered complex."""
+    seed_all()
+    X = fb.generate_noisy_torus_points_3d(num_witnesses).to(DEV)
+    L = fb.generate_landmarks(X, num_landmarks)
+    if return_simplex_tree:
+        st = fb.flood_complex(X, L, return_simplex_tree=True)
+    else:
+        fc = fb.flood_complex(X, L, return_simplex_tree=False)
+        st = fb.SimplexTree()
+        for simplex in fc:
+            st.insert(simplex, float("inf"))
+            st.assign_filtration(simplex, fc[simplex])
+    for simplex, filtration in st.get_simplices():
+        faces = list(st.get_boundaries(simplex))
+        assert len(faces) == (len(simplex) if len(simplex) > 1 else 0)
+        for face, face_filtration in faces:
+            assert face_filtration <= filtration
+
+
+@pytest.mark.parametrize("pointcloud", ["torus", "cheese"])
+def test_float64_inputs(pointcloud):
+    """Reference tests/test_flooder.py:214-246 (f32 vs f64 within 3e-6)."""
+    seed_all()
+    pts = fb.generate_noisy_torus_points_3d(50_000) if pointcloud == "torus" else fb.generate_swiss_cheese_points(50_000)[0]
+    seed_all()
+    lms = fb.generate_landmarks(pts.to(DEV), 500)
+    flood32 = fb.flood_complex(pts.to(DEV), lms)
+    with pytest.warns(RuntimeWarning):
+        flood64 = fb.flood_complex(pts.to(DEV, torch.float64), lms.to(torch.float64))
+    for s in flood32:
+        assert abs(flood32[s] - flood64[s]) < 3e-6
+
+
+def test_vs_exact_alpha_free_property_2d():
+    """With L = X every landmark is a cloud point: all vertex values are exactly 0 and every
+    edge value is at most half its length (the midpoint is within len/2 of both endpoints)."""
+    seed_all()
+    X = fb.generate_figure_eight_points_2d(1000).to(DEV)
+    fc = fb.flood_complex(X, X, points_per_edge=31, batch_size=8)
+    Xc = X.cpu().numpy().astype(np.float64)
+    for s, f in fc.items():
+        if len(s) == 1:
+            assert f == 0.0
+        elif len(s) == 2:
+            assert f <= 0.5 * np.linalg.norm(Xc[s[0]] - Xc[s[1]]) * (1 + 1e-5) + 1e-7
+
+
+def test_errors_match_reference():
+    X = torch.rand(100, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="must be positive"):
+        fb.generate_landmarks(X, 0)
+    with pytest.raises(RuntimeError, match="landmarks.device"):
+        fb.flood_complex(X, X[:10].cpu())
+    with pytest.raises(RuntimeError, match="landmarks.dtype"):
+        fb.flood_complex(X, X[:10].double())
+    with pytest.raises(TypeError, match="not supported"):
+        fb.flood_complex(X.half(), X[:10].half())
+    with pytest.raises(RuntimeError, match="Device not supported"):
+        fb.flood_complex(X.cpu(), X[:10].cpu())
