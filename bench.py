@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Benchmark of the Flood-complex hot path (BASELINE.json: point-simplex distance evaluations/s
+and flood_complex wall time; noisy torus 1 M points, 1 k landmarks, 3-D, 30 points per edge).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement"):
+
+* unit of work = one evaluation = (sample point on a simplex, cloud point inside the simplex's
+  reference bounding ball) squared distance + running-min update; the algorithmic count
+  E = sum_s R * |ball(s) & cloud| is produced by the kernel's own counter and does not depend
+  on tiling or padding.
+* step = one pass of the device path over the whole job: cloud grid build, bounding balls,
+  covering-radius kernel, per-face maxima (and the NCCL all-gather of the per-simplex values
+  when N > 1); the simplex list is sharded over the N ranks, the cloud is replicated
+  (strong scaling: the job is fixed).
+* value = E * K / (sum of the K per-step device times, CUDA events, max over ranks).
+* e2e = the same metric through the public API: pinned-host cloud -> device copy +
+  flood_complex(points, n_landmarks) (FPS, host Delaunay, kernels, device->host read of the
+  values, assembly of the complex), wall clock with synchronisation on both sides.
+* roofline: FP32 issue slots of the direct-difference form, 2D+1 = 7 per evaluation
+  (SURVEY.md section 8d); peak = SMs x 128 lanes x max SM clock.
+* cpu_baseline / --impl reference: the reference's CPU path (exact KD-tree nearest neighbour
+  per sample point, scipy, one thread as in the reference) restated in oracle/, timed on a
+  bounded sample of the same job's simplices.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "point-simplex distance evaluations/s (flood_complex, noisy torus 1M pts, 1k landmarks, 3D)"
+UNIT = "evals/s"
+WORKLOADS = {
+    # name: (generator, n_points, n_landmarks, dim, points_per_edge)
+    "torus_1m_1k": ("torus", 1_000_000, 1000, 3, 30),
+    "torus_10k_100": ("torus", 10_000, 100, 3, 30),
+    "gauss_10m_5k": ("gauss", 10_000_000, 5000, 3, 30),
+}
+KERNELS_PER_STEP = 12  # cloud build 6, balls 1, covering 4 (fill, plan, scan, eval), face max 1
+SLOTS_PER_EVAL = {2: 5, 3: 7, 4: 9, 5: 11, 6: 13}
+
+
+def make_cloud(kind: str, n: int, dim: int):
+    import torch
+
+    import flooder_b200 as fb
+
+    torch.manual_seed(42)
+    np.random.seed(42)
+    if kind == "torus":
+        return fb.generate_noisy_torus_points_3d(n)
+    if kind == "gauss":
+        return torch.randn(n, dim)
+    raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001  (nvidia-smi missing)
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        rows = []
+        with open(self.path) as fh:
+            for line in fh:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 9:
+                    rows.append(parts)
+        os.unlink(self.path)
+        if not rows:
+            return None
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None,
+                "sm_max_mhz": float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's CPU path)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(points: np.ndarray, simplex_vertices: np.ndarray, weights: np.ndarray,
+                         cand_counts: np.ndarray, tree=None, workers: int = 1):
+    """Time the reference's CPU distance step (flooder/core.py:197-199: one KDTree.query over all
+    sample points, float64) on the given simplices; returns (seconds, evaluations, tree)."""
+    from scipy.spatial import KDTree
+
+    from oracle import flood_oracle
+
+    if tree is None:
+        tree = KDTree(points)
+    t0 = time.perf_counter()
+    x = flood_oracle.sample_points(weights, simplex_vertices)             # core.py:188
+    dist, _ = tree.query(x.reshape(-1, x.shape[-1]), workers=workers)     # core.py:197-199
+    _ = dist.reshape(x.shape[0], x.shape[1]).max(axis=1)
+    dt = time.perf_counter() - t0
+    evals = int(cand_counts.sum()) * weights.shape[0]
+    return dt, evals, tree
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import flood_oracle, native
+    from oracle.simplex_tree import delaunay_top_simplices
+
+    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
+    pts = make_cloud(kind, n, dim).numpy()
+    lms = pts[native.fps(pts, n_lms, 0)]
+    cells = delaunay_top_simplices(lms)
+    weights, _, _ = flood_oracle.generate_grid(ppe, dim)
+    rng = np.random.default_rng(0)
+    per_step = args.ref_simplices_per_step
+    order = rng.permutation(len(cells))
+    verts_all = lms[cells]
+    centers, radii = flood_oracle.bounding_balls(verts_all, dim)
+    from scipy.spatial import KDTree
+
+    t0 = time.perf_counter()
+    tree = KDTree(pts)                                                    # core.py:128
+    build_s = time.perf_counter() - t0
+    times, evals = [], []
+    for step in range(args.warmup + args.steps):
+        sel = order[(step * per_step) % len(cells):][:per_step]
+        counts = native.ball_counts(pts, centers[sel], radii[sel])
+        dt, ev, _ = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree=tree, workers=1)
+        if step >= args.warmup:
+            times.append(dt)
+            evals.append(ev)
+    total_t, total_e = float(np.sum(times)), float(np.sum(evals))
+    value = total_e / total_t
+    # one extra sample with every host thread, for context
+    sel = order[:per_step]
+    counts = native.ball_counts(pts, centers[sel], radii[sel])
+    dt_all, ev_all, _ = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree=tree, workers=-1)
+    sample = (f"{per_step} of {len(cells)} simplices per step (random, seeded), {weights.shape[0]} samples each, "
+              f"KD-tree over the full {n}-point cloud built once outside the steps ({build_s:.2f} s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "value_all_host_threads": ev_all / dt_all,
+                         "note": "reference calls scipy KDTree.query without workers= (single thread); "
+                                 "value_all_host_threads uses workers=-1"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, extra):
+    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
+    cfg = {"workload": f"noisy torus {n} points, {n_lms} landmarks, {dim}D (BASELINE.json configs[1])"
+           if args.workload == "torus_1m_1k" else args.workload,
+           "n_points": n, "n_landmarks": n_lms, "dim": dim, "points_per_edge": ppe,
+           "parallelism": f"simplices sharded over {args.gpus} GPU(s), cloud replicated",
+           "l2": "flushed between timed steps (256 MiB write)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# the CUDA arm
+# --------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    import flooder_b200 as fb
+    from flooder_b200 import _native
+    from flooder_b200 import distributed as fdist
+    from flooder_b200.core import _support_masks
+    from flooder_b200.simplex_tree import delaunay_cells
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ext = _native.ext()
+    ext.set_option("time_kernels", 1)
+
+    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
+    host_pts = make_cloud(kind, n, dim).pin_memory()
+    pts = host_pts.to(dev, non_blocking=True)
+    lms = pts[ext.fps(pts, n_lms, 0)]
+    cells = delaunay_cells(lms.cpu().numpy())
+    S_total = len(cells)
+    verts_all = lms[torch.as_tensor(cells, device=dev)].contiguous()
+    weights, _, _ = fb.generate_grid(ppe, dim, dev)
+    support = _support_masks(weights)
+    R, K = weights.shape
+    if world > 1:
+        parts = fdist.partition(fdist.cost_proxy(verts_all), world)
+        mine = parts[rank]
+        shard = fdist.Shard(rank, world)
+    else:
+        parts, mine, shard = None, None, None
+    verts = verts_all if mine is None else verts_all[mine].contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def device_step():
+        ws = ext.cloud_build(pts, 0)
+        c, r = ext.bounding_balls(verts)
+        md2, cnt, ev = ext.covering_radius(ws, n, dim, verts, weights, None, c, r)
+        vals = ext.face_max(md2, support, K)
+        if shard is not None:
+            vals = fdist.gather_rows(vals, parts, shard)
+        return vals, ev
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+        flush.fill_(1)
+    barrier()
+    ext.kernel_ms("cover_eval", True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    step_ms, evals_local = [], 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _, ev = device_step()
+        b.record()
+        b.synchronize()
+        step_ms.append(a.elapsed_time(b))
+        evals_local = int(ev.item())
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    clock_info = clocks.stop() if rank == 0 else None
+    eval_ms_total, eval_launches = ext.kernel_ms("cover_eval", True)
+
+    total_ms = torch.tensor([float(np.sum(step_ms))], device=dev, dtype=torch.float64)
+    evals_t = torch.tensor([float(evals_local)], device=dev, dtype=torch.float64)
+    eval_ms_t = torch.tensor([eval_ms_total / max(1, eval_launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(eval_ms_t, op=dist.ReduceOp.MAX)
+    E = evals_t.item()                      # whole job, per step
+    ms_per_step = total_ms.item() / args.steps
+    value = E / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API --------------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host_lms_bytes = n_lms * dim * 4
+    fb.flood_complex(host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dpts = host_pts.to(dev, non_blocking=True)                      # H2D from pinned memory
+        res = fb.flood_complex(dpts, n_lms, points_per_edge=ppe)       # includes D2H of the values
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = e2e_t.item()
+    n_simplices = len(res)
+
+    if rank == 0:
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        slots = SLOTS_PER_EVAL[dim]
+        peak_slots = sm_count * 128 * sm_max_mhz * 1e6
+        # dominant kernel: evaluations of the slowest rank's launch / its event time
+        per_launch_evals = E / world
+        kernel_rate = per_launch_evals / (eval_ms_t.item() * 1e-3)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
+        except OSError:
+            pass
+        roofline = {
+            "bound": "fp32-issue (CUDA-core FP32 lane slots; neither HBM nor tensor: contraction length is D=3)",
+            "kernel": "cover_eval_kernel",
+            "achieved": kernel_rate * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
+            "frac": kernel_rate * slots / peak_slots,
+            "traffic": traffic,
+            "slots_per_eval": slots, "evals_per_launch": per_launch_evals,
+            "kernel_ms_per_launch": eval_ms_t.item(), "kernel_evals_per_s": kernel_rate,
+            "peak_evals_per_s": peak_slots / slots,
+            "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
+            "flop_view": {"achieved_tflops": kernel_rate * (3 * dim - 1) / 1e12,
+                          "peak_tflops": 2 * peak_slots / 1e12},
+            "hbm_view": {"algorithmic_bytes_per_launch": 16.0 * n + 4.0 * (S_total / world) * R,
+                         "peak_gbs": peaks.get("hbm_gbs")},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, {"simplices": S_total, "samples_per_simplex": int(R),
+                                         "evals_per_step": E, "returned_simplices": n_simplices}),
+            "e2e": {"value": E / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * dim * 4 * world),
+                    "d2h_bytes_per_step": int((S_total * (2 ** K - 1) * 4 + host_lms_bytes) * world),
+                    "flood_complex_wall_s": e2e_s, "steps": e2e_steps,
+                    "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps * world,
+            "roofline": roofline,
+            "clocks": clock_info,
+            "timed_region_wall_s": wall_s,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, host_pts.numpy(), lms.cpu().numpy(), cells,
+                                                weights.cpu().numpy())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, pts, lms, cells, weights):
+    """Oracle port of the reference CPU path on a bounded sample of this job (rank 0, N = 1)."""
+    from scipy.spatial import KDTree
+
+    from oracle import flood_oracle, native
+
+    dim = pts.shape[1]
+    rng = np.random.default_rng(0)
+    sel = rng.permutation(len(cells))[: args.cpu_sample_simplices]
+    verts = lms[cells[sel]]
+    centers, radii = flood_oracle.bounding_balls(verts, dim)
+    counts = native.ball_counts(pts, centers, radii)
+    t0 = time.perf_counter()
+    tree = KDTree(pts)
+    build_s = time.perf_counter() - t0
+    dt, evals, _ = cpu_reference_sample(pts, verts, weights, counts, tree=tree, workers=1)
+    return {"value": evals / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{len(sel)} of {len(cells)} simplices (random, seeded), {weights.shape[0]} samples each; "
+                      f"scipy KDTree.query single-threaded as in the reference ({dt:.1f} s) over a tree of the "
+                      f"full cloud (build {build_s:.1f} s, not included)",
+            "host_cores": os.cpu_count(),
+            "projected_full_job_s": build_s + dt * len(cells) / len(sel)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="torus_1m_1k", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-simplices", type=int, default=200)
+    ap.add_argument("--ref-simplices-per-step", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,7 @@ def cdll() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "flood_abi_version", "flood_last_error", "flood_device_info", "flood_set_option",
+    "flood_abi_version", "flood_last_error", "flood_device_info", "flood_set_option", "flood_kernel_ms",
     "flood_fps_workspace_bytes", "flood_fps_f32",
     "flood_cloud_workspace_bytes", "flood_cloud_build_f32",
     "flood_bounding_balls_f32",

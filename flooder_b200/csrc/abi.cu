@@ -29,6 +29,39 @@ int get_option(const char *name, int fallback) {
     return it == g_options.end() ? fallback : it->second;
 }
 
+struct KernelTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    double total_ms = 0.0;
+    long launches = 0;
+    bool pending = false;
+};
+static std::map<std::string, KernelTimer> g_timers;
+
+static void timer_collect(KernelTimer &t) {
+    if (!t.pending) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+        t.total_ms += ms;
+        t.launches += 1;
+    }
+    t.pending = false;
+}
+
+void kernel_timer_start(const char *name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_opt_mutex);
+    KernelTimer &t = g_timers[name];
+    if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+    timer_collect(t);  // one launch in flight per timer: fold the previous one in first
+    cudaEventRecord(t.a, st);
+}
+
+void kernel_timer_stop(const char *name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_opt_mutex);
+    KernelTimer &t = g_timers[name];
+    cudaEventRecord(t.b, st);
+    t.pending = true;
+}
+
 int device_sm_count() {
     static thread_local int cached_dev = -1, cached_sms = 0;
     int dev = 0;
@@ -69,6 +102,22 @@ int flood_set_option(const char *name, int value) {
     if (it != g_options.end()) prev = it->second;
     g_options[name] = value;
     return prev;
+}
+
+int flood_kernel_ms(const char *name, double *total_ms, long *launches, int reset) {
+    if (!name) return FLOOD_E_INVALID;
+    std::lock_guard<std::mutex> lock(g_opt_mutex);
+    auto it = g_timers.find(name);
+    if (it == g_timers.end()) {
+        if (total_ms) *total_ms = 0.0;
+        if (launches) *launches = 0;
+        return FLOOD_OK;
+    }
+    timer_collect(it->second);
+    if (total_ms) *total_ms = it->second.total_ms;
+    if (launches) *launches = it->second.launches;
+    if (reset) { it->second.total_ms = 0.0; it->second.launches = 0; }
+    return FLOOD_OK;
 }
 
 size_t flood_fps_workspace_bytes(int64_t n, int d, int64_t n_lms) { return fps_workspace_bytes(n, d, n_lms); }

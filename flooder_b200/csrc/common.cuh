@@ -35,6 +35,9 @@ int set_error(int code, const char *fmt, ...);
     } while (0)
 
 int get_option(const char *name, int fallback);
+// optional CUDA-event timing of individual kernels (option "time_kernels"); see flood_kernel_ms
+void kernel_timer_start(const char *name, cudaStream_t st);
+void kernel_timer_stop(const char *name, cudaStream_t st);
 int device_sm_count();
 
 // --------------------------------------------------------------------------------------

@@ -457,7 +457,10 @@ int launch_eval(const CoverParams &P, int nwarps, cudaStream_t st) {
     const int cap = get_option("ctas_per_sm", 0);
     if (cap > 0 && per_sm > cap) per_sm = cap;
     const int grid = device_sm_count() * per_sm;
+    const bool timed = get_option("time_kernels", 0) != 0;
+    if (timed) kernel_timer_start("cover_eval", st);
     kern<<<grid, nwarps * 32, 0, st>>>(P);
+    if (timed) kernel_timer_stop("cover_eval", st);
     FLOOD_LAUNCH_CHECK("cover_eval_kernel");
     return FLOOD_OK;
 }

@@ -163,7 +163,10 @@ int launch_fps(FpsParams &P, cudaStream_t st, bool probe_only, long long *capaci
     if (capacity) *capacity = (long long)grid * threads * (PPT > 0 ? PPT : 0);
     if (probe_only) return FLOOD_OK;
     void *args[] = {(void *)&P};
+    const bool timed = get_option("time_kernels", 0) != 0;
+    if (timed) kernel_timer_start("fps", st);
     FLOOD_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(threads), args, 0, st));
+    if (timed) kernel_timer_stop("fps", st);
     return FLOOD_OK;
 }
 
@@ -179,7 +182,7 @@ int dispatch_fps(FpsParams &P, cudaStream_t st) {
         if (P.n <= cap) return launch_fps<D, 2>(P, st, false, nullptr);
         if ((rc = launch_fps<D, 4>(P, st, true, &cap)) != FLOOD_OK) return rc;
         if (P.n <= cap) return launch_fps<D, 4>(P, st, false, nullptr);
-        if (D <= 4) {
+        if constexpr (D <= 4) {
             if ((rc = launch_fps<D, 8>(P, st, true, &cap)) != FLOOD_OK) return rc;
             if (P.n <= cap) return launch_fps<D, 8>(P, st, false, nullptr);
         }

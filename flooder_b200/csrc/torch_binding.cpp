@@ -130,6 +130,13 @@ torch::Tensor face_max(const torch::Tensor &min_dist2, const c10::optional<torch
     return out;
 }
 
+std::tuple<double, int64_t> kernel_ms(const std::string &name, bool reset) {
+    double ms = 0.0;
+    long launches = 0;
+    check(flood_kernel_ms(name.c_str(), &ms, &launches, reset ? 1 : 0), "flood_kernel_ms");
+    return {ms, (int64_t)launches};
+}
+
 int64_t set_option(const std::string &name, int64_t value) { return flood_set_option(name.c_str(), (int)value); }
 
 }  // namespace
@@ -143,4 +150,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("covering_radius", &covering_radius);
     m.def("face_max", &face_max);
     m.def("set_option", &set_option);
+    m.def("kernel_ms", &kernel_ms);
 }

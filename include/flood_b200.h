@@ -116,6 +116,11 @@ int flood_face_max_f32(const float *min_dist2, int64_t S, int64_t R, const int32
 /* Tuning knobs for experiments (process-wide; return the previous value).  */
 int flood_set_option(const char *name, int value);
 
+/* With option "time_kernels" = 1 the library brackets its dominant kernels with CUDA events on the
+ * launching stream.  flood_kernel_ms() synchronises on the last recorded launch of `name`
+ * ("cover_eval", "fps") and reports the accumulated device time and launch count. */
+int flood_kernel_ms(const char *name, double *total_ms, long *launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,167 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/flood_b200.h
+declares (no compute without a GPU), the host logic of the package, and the no-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import flooder_b200 as fb
+from flooder_b200 import _native, core
+from flooder_b200.simplex_tree import SimplexTree, delaunay_cells, faces_of_cells
+from oracle import flood_oracle
+from oracle.simplex_tree import DictSimplexTree, delaunay_top_simplices
+from tests.helpers import load_golden, seed_all
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "flood_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(flood_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    declared = _declared_symbols()
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in flood_b200.h but not exported"
+    assert _native.cdll().flood_abi_version() == 1
+
+
+def test_abi_argument_validation_without_gpu():
+    """Argument checks run before any CUDA call, so they are testable on a CPU box."""
+    lib = _native.cdll()
+    assert lib.flood_cloud_workspace_bytes(0, 3) == 0
+    assert lib.flood_cloud_workspace_bytes(1000, 9) == 0
+    assert lib.flood_cloud_workspace_bytes(1_000_000, 3) > 16_000_000
+    assert lib.flood_fps_workspace_bytes(1000, 3, 10) >= 1000 * 4
+    rc = lib.flood_fps_f32(None, 10, 3, 5, 0, None, None, 0, None)
+    assert rc == -1 and b"bad arguments" in lib.flood_last_error()
+    rc = lib.flood_covering_radius_f32(None, 10, 3, None, 5, 4, None, 10, None, None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    rc = lib.flood_bounding_balls_f32(None, 5, 4, 3, None, None, None)
+    assert rc == -1
+
+
+def test_torch_extension_loads():
+    ext = _native.ext()
+    assert ext.abi_version() == 1
+    for fn in ("fps", "cloud_build", "bounding_balls", "covering_radius", "face_max", "kernel_ms"):
+        assert hasattr(ext, fn)
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing elsewhere."""
+    x = torch.rand(50, 3)
+    with pytest.raises(RuntimeError, match="Device not supported|CUDA"):
+        fb.flood_complex(x, x[:8])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _native.ext().fps(x, 4, 0)
+    src = open(os.path.join(ROOT, "flooder_b200", "core.py")).read()
+    assert "oracle" not in src and "KDTree" not in src
+
+
+def test_product_does_not_import_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "flooder_b200")):
+        if fn.endswith(".py"):
+            text = open(os.path.join(ROOT, "flooder_b200", fn)).read()
+            assert "import oracle" not in text and "from oracle" not in text, fn
+
+
+def test_generate_grid_matches_oracle():
+    for n, dim in [(30, 3), (130, 2), (20, 3), (6, 5), (4, 6), (5, 1)]:
+        w, vidx, fidx = fb.generate_grid(n, dim, "cpu")
+        wo, vo, fo = flood_oracle.generate_grid(n, dim)
+        np.testing.assert_array_equal(w.numpy(), wo)
+        for a, b in zip(fidx, fo):
+            np.testing.assert_array_equal(a.numpy(), b)
+        for a, b in zip(vidx, vo):
+            np.testing.assert_array_equal(a.numpy(), b)
+
+
+def test_uniform_weights_match_oracle():
+    seed_all(7)
+    a = fb.generate_uniform_weights(100, 3, "cpu").numpy()
+    seed_all(7)
+    b = flood_oracle.generate_uniform_weights(100, 3)
+    np.testing.assert_array_equal(a, b)
+    assert (fb.generate_uniform_weights(5, 0, "cpu").numpy() == 1).all()
+
+
+def test_support_masks_select_reference_faces():
+    """Samples with support inside face m == the reference's face_idxs rows for that face."""
+    w, vidx, fidx = fb.generate_grid(9, 3, "cpu")
+    sup = core._support_masks(w).numpy()
+    for rows, vsel in zip(fidx, vidx):
+        for j in range(rows.shape[0]):
+            m = sum(1 << int(k) for k in vsel[j])
+            mine = np.nonzero((sup & ~m) == 0)[0]
+            np.testing.assert_array_equal(mine, rows[j].numpy())
+
+
+def test_collect_faces_min_over_cofaces():
+    cells = np.array([[0, 1, 2], [1, 2, 3]])
+    vals = np.arange(14, dtype=np.float32).reshape(2, 7)
+    out = {}
+    core._collect_faces(cells, vals, out)
+    assert out[(0, 1, 2)] == 6 and out[(1, 2, 3)] == 13
+    assert out[(1, 2)] == min(vals[0, 0b110 - 1], vals[1, 0b011 - 1])
+    assert out[(0,)] == vals[0, 0] and out[(3,)] == vals[1, 0b100 - 1]
+    assert len(out) == 4 + 5 + 2
+
+
+@pytest.mark.parametrize("name", ["virus", "coral", "lockwasher"])
+def test_delaunay_matches_shipped_gudhi_sets(name):
+    g = load_golden("shipped_" + name)
+    cells = delaunay_cells(g["landmarks"])
+    assert {tuple(r) for r in cells.tolist()} == {tuple(r) for r in g["tetrahedra"].tolist()}
+    assert {tuple(r) for r in faces_of_cells(cells, 3).tolist()} == {tuple(r) for r in g["triangles"].tolist()}
+    assert {tuple(r) for r in faces_of_cells(cells, 2).tolist()} == {tuple(r) for r in g["edges"].tolist()}
+
+
+def test_simplex_tree_matches_oracle_tree():
+    rng = np.random.default_rng(1)
+    pts = rng.random((60, 3))
+    cells = delaunay_cells(pts)
+    np.testing.assert_array_equal(np.unique(cells, axis=0), np.unique(delaunay_top_simplices(pts), axis=0))
+    a, b = SimplexTree.from_cells(cells), DictSimplexTree.from_top_simplices(cells)
+    assert a.num_simplices() == b.num_simplices() and a.num_vertices() == 60 and a.dimension() == 3
+    keys = [tuple(s) for s, _ in a.get_simplices()]
+    assert keys == [tuple(s) for s, _ in b.get_simplices()]
+    vals = rng.random(len(keys))
+    for k, v in zip(keys, vals):
+        if len(k) != 3:            # leave the triangles unassigned (NaN)
+            a.assign_filtration(k, v)
+            b.assign_filtration(k, v)
+    assert a.make_filtration_non_decreasing() == b.make_filtration_non_decreasing()
+    for (s, f), (s2, f2) in zip(a.get_simplices(), b.get_simplices()):
+        assert s == s2 and (f == f2 or (np.isnan(f) and np.isnan(f2)))
+    for s, f in a.get_simplices():
+        for face, ff in a.get_boundaries(s):
+            assert not ff > f
+    with pytest.raises(KeyError):
+        a.assign_filtration((0, 59, 58, 57, 56), 1.0)
+
+
+def test_synthetic_generators_match_reference_bytes():
+    g = load_golden("ref_generators")
+    seed_all()
+    np.testing.assert_array_equal(fb.generate_noisy_torus_points_3d(64).numpy(), g["torus"])
+    seed_all()
+    np.testing.assert_array_equal(fb.generate_figure_eight_points_2d(64).numpy(), g["fig8"])
+    seed_all()
+    np.testing.assert_array_equal(fb.generate_swiss_cheese_points(64)[0].numpy(), g["cheese"])
+    seed_all()
+    np.testing.assert_array_equal(fb.generate_annulus_points_2d(64).numpy(), g["annulus"])
+
+
+def test_landmark_argument_errors():
+    with pytest.raises(RuntimeError, match="must be positive"):
+        fb.generate_landmarks(torch.rand(10, 2), 0)
+    with pytest.raises(RuntimeError, match="must be positive"):
+        fb.generate_landmarks(torch.rand(10, 2), -3)
