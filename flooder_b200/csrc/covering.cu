@@ -193,6 +193,13 @@ template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel()
     return r;
 }
 
+// 3-input minimum (FMNMX3 on sm_100a)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // squared distance, direct difference form: (x0-p0)^2 rounded, then FMA accumulation
 template <int D>
 __device__ __forceinline__ float dist2(const float (&x)[D], const float (&p)[D]) {
@@ -324,7 +331,12 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             }
         }
 
-        // sweep of the shared tile by all warps: the hot loop
+        // sweep of the shared tile by all warps: the hot loop.  Two samples share one packed
+        // FP32x2 instruction (FADD2 / FMUL2 / FFMA2 take the candidate coordinate as a broadcast
+        // scalar operand), two candidates share one 3-input FMNMX3: per pair of samples and pair
+        // of candidates that is 2 x (D FADD2 + FMUL2 + (D-1) FFMA2) + 2 FMNMX3 issue slots for four
+        // evaluations.  Each lane result is the same IEEE operation as the scalar form
+        // (x - p, round; * , round; fma, round), so the minima are bit-identical.
         auto sweep = [&](int n) {
             const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
             if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
@@ -335,9 +347,25 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
+                for (int u = 0; u < kUnroll; u += 2) {
 #pragma unroll
-                    for (int t = 0; t < T; ++t) m[t] = fminf(m[t], dist2<D>(x[t], p[u]));
+                    for (int t = 0; t < T; t += 2) {
+                        float2 acc[2];
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            float2 df = __fadd2_rn(make_float2(x[t][0], x[t + 1][0]),
+                                                   make_float2(-p[u + v][0], -p[u + v][0]));
+                            acc[v] = __fmul2_rn(df, df);
+#pragma unroll
+                            for (int a = 1; a < D; ++a) {
+                                df = __fadd2_rn(make_float2(x[t][a], x[t + 1][a]),
+                                                make_float2(-p[u + v][a], -p[u + v][a]));
+                                acc[v] = __ffma2_rn(df, df, acc[v]);
+                            }
+                        }
+                        m[t] = fmin3(m[t], acc[0].x, acc[1].x);
+                        m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
+                    }
                 }
             }
             __syncthreads();

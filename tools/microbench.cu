@@ -27,6 +27,51 @@ __global__ void __launch_bounds__(640, 1) mix_kernel(const float4 *__restrict__ 
         z[t] = blockIdx.x * 0.003f + t;
         m[t] = 1e30f;
     }
+    if (VARIANT >= 5) {
+        // software-pipelined: the next trip's candidates are fetched before the current math
+        for (int it = 0; it < iters; ++it) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = tile[u];
+#pragma unroll 1
+            for (int j = 0; j < TILE; j += 4) {
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = q[u];
+                const int jn = (j + 4) & (TILE - 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = tile[jn + u];
+                if (VARIANT == 5) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            float dx = x[t] - p[u].x, dy = y[t] - p[u].y, dz = z[t] - p[u].z;
+                            m[t] = fminf(m[t], fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                        }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u += 2)
+#pragma unroll
+                        for (int t = 0; t < T; t += 2) {
+                            float2 s[2];
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                const float4 c = p[u + v];
+                                float2 dx = __fadd2_rn(make_float2(x[t], x[t + 1]), make_float2(-c.x, -c.x));
+                                float2 dy = __fadd2_rn(make_float2(y[t], y[t + 1]), make_float2(-c.y, -c.y));
+                                float2 dz = __fadd2_rn(make_float2(z[t], z[t + 1]), make_float2(-c.z, -c.z));
+                                float2 a = __fmul2_rn(dx, dx);
+                                a = __ffma2_rn(dy, dy, a);
+                                s[v] = __ffma2_rn(dz, dz, a);
+                            }
+                            m[t] = min3(m[t], s[0].x, s[1].x);
+                            m[t + 1] = min3(m[t + 1], s[0].y, s[1].y);
+                        }
+                }
+            }
+        }
+    } else
     for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
         for (int j = 0; j < TILE; j += 4) {
@@ -97,8 +142,8 @@ __global__ void __launch_bounds__(640, 1) mix_kernel(const float4 *__restrict__ 
 }
 
 template <int V>
-void run(const char *name, const float4 *cand, float *out, int sms, double slots_per_pair) {
-    const int iters = 40, threads = 640;
+void run(const char *name, const float4 *cand, float *out, int sms, double slots_per_pair, int threads = 640) {
+    const int iters = 40;
     mix_kernel<V><<<sms, threads>>>(cand, out, 2);
     cudaDeviceSynchronize();
     cudaEvent_t a, b;
@@ -114,8 +159,8 @@ void run(const char *name, const float4 *cand, float *out, int sms, double slots
     }
     double pairs = (double)sms * threads * T * (double)TILE * iters;
     double rate = pairs / (best * 1e-3);
-    printf("%-28s %8.3f ms  %.3e pairs/s  (= %.1f%% of the 7-slot roofline at 1.965 GHz; %.2f slots/pair nominal)\n",
-           name, best, rate, 100.0 * rate / (sms * 128.0 * 1.965e9 / 7.0), slots_per_pair);
+    printf("[%4d thr] %-28s %8.3f ms  %.3e pairs/s  (= %.1f%% of the 7-slot roofline at 1.965 GHz; %.2f slots/pair nominal)\n",
+           threads, name, best, rate, 100.0 * rate / (sms * 128.0 * 1.965e9 / 7.0), slots_per_pair);
 }
 
 int main() {
@@ -131,6 +176,16 @@ int main() {
     run<2>("packed f32x2 + min3 (3.5)", cand, out, sms, 3.5);
     run<3>("norm expansion (4)", cand, out, sms, 4);
     run<4>("7 x FFMA probe", cand, out, sms, 7);
+    run<5>("scalar, sw-pipelined", cand, out, sms, 7);
+    run<6>("packed+min3, sw-pipelined", cand, out, sms, 3.5);
+    const int sweep[] = {128, 256, 384, 512};
+    for (int th : sweep) {
+        run<0>("scalar (7 slots)", cand, out, sms, 7, th);
+        run<5>("scalar, sw-pipelined", cand, out, sms, 7, th);
+        run<2>("packed f32x2 + min3", cand, out, sms, 3.5, th);
+        run<6>("packed+min3, sw-pipelined", cand, out, sms, 3.5, th);
+        run<4>("7 x FFMA probe", cand, out, sms, 7, th);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
