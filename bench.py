@@ -199,6 +199,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_triton(args):
+    """--impl reference_triton (informative, not part of the driver contract): the UNMODIFIED
+    reference package installed under baseline/_ref, its own Triton path on this GPU
+    (flooder/core.py:193-226 with batch_size=64 as in examples/example_02_torus_3d.py), with the
+    gudhi/fpsample stand-ins of oracle/ref_shims.py.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+
+    from oracle import ref_shims
+
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        fl = ref_shims.import_reference(ref_root)
+    except ImportError as exc:
+        print(json.dumps({"impl": "reference_triton", "unavailable": str(exc)}), flush=True)
+        return
+    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
+    pts = make_cloud(kind, n, dim)
+    dev = torch.device("cuda")
+    lms = fl.generate_landmarks(pts, n_lms, start_idx=0).to(dev)
+    dpts = pts.to(dev)
+    # instrument the two Triton entry points to split out kernel time and count the work
+    core = fl.core
+    stats = {"mask_ms": 0.0, "filt_ms": 0.0, "nonzero_ms": 0.0, "cand": 0}
+    orig_mask, orig_filt = core.compute_mask, core.compute_filtration
+
+    def timed(fn, key):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            e1.synchronize()
+            stats[key] += e0.elapsed_time(e1)
+            return out
+        return wrapper
+
+    fl.flood_complex(dpts[:10000], lms, use_triton=True, points_per_edge=ppe)   # warm-up as in the examples
+    torch.cuda.synchronize()
+    walls = []
+    for _ in range(max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    # instrumented pass (kernel split + algorithmic work count)
+    def mask_counting(points, centers, radii, *rest):
+        out = timed(orig_mask, "mask_ms")(points, centers, radii, *rest)
+        stats["cand"] += int(out[:, : points.shape[0]].sum().item())
+        return out
+    core.compute_mask = mask_counting
+    core.compute_filtration = timed(orig_filt, "filt_ms")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
+    torch.cuda.synchronize()
+    instrumented_wall = time.perf_counter() - t0
+    core.compute_mask, core.compute_filtration = orig_mask, orig_filt
+    from math import comb
+
+    R = comb(ppe + dim - 1, dim)
+    E = stats["cand"] * R
+    wall = float(np.median(walls))
+    print(json.dumps({
+        "impl": "reference_triton", "metric": METRIC, "value": E / (stats["filt_ms"] * 1e-3), "unit": UNIT,
+        "n_gpus": 1, "config": config_dict(args, {"batch_size": 64, "evals_per_step": E, "simplices_returned": len(res)}),
+        "e2e": {"value": E / wall, "unit": UNIT, "flood_complex_wall_s": wall, "walls": walls},
+        "kernel_ms": {"compute_filtration": stats["filt_ms"], "compute_mask": stats["mask_ms"]},
+        "instrumented_wall_s": instrumented_wall,
+        "note": "value = E / time inside the reference's compute_filtration Triton kernel; e2e = E / flood_complex "
+                "wall on device-resident inputs (landmarks precomputed), median of the listed runs",
+    }), flush=True)
+
+
 def config_dict(args, extra):
     kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
     cfg = {"workload": f"noisy torus {n} points, {n_lms} landmarks, {dim}D (BASELINE.json configs[1])"
@@ -413,7 +489,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference", "reference_triton"])
     ap.add_argument("--workload", default="torus_1m_1k", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-simplices", type=int, default=200)
@@ -422,6 +498,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference_triton":
+        run_reference_triton(args)
     else:
         run_cuda(args)
 

@@ -21,7 +21,7 @@ import torch
 
 from . import _native
 from . import distributed as fdist
-from .simplex_tree import HAS_GUDHI, SimplexTree, delaunay_simplex_tree
+from .simplex_tree import FaceTable, SimplexTree, delaunay_complex
 
 _SUPPORTED_DTYPES = (torch.float32, torch.float64)
 
@@ -74,6 +74,19 @@ def generate_uniform_weights(num_rand: int, dim: int, device, dtype=torch.float3
         return torch.ones((num_rand, 1), device=device, dtype=dtype)
     w = -torch.log(1 - torch.rand(num_rand, dim + 1)).to(device, dtype=dtype)
     return w / w.sum(dim=1, keepdim=True)
+
+
+@functools.lru_cache(maxsize=16)
+def _grid_weights_cached(n: int, dim: int, device_str: str) -> torch.Tensor:
+    counts = torch.as_tensor(_lattice(n, dim), device=device_str)
+    weights = torch.empty(counts.shape, dtype=torch.float32, device=device_str)
+    torch.divide(counts, n - 1, out=weights)
+    return weights
+
+
+def _grid_weights(n: int, dim: int, device) -> torch.Tensor:
+    """The weights of ``generate_grid`` only (cached per device; treated as read-only)."""
+    return _grid_weights_cached(int(n), int(dim), str(device))
 
 
 def _support_masks(weights: torch.Tensor) -> torch.Tensor:
@@ -171,26 +184,16 @@ def covering_values(
     return values
 
 
-def _face_columns(K: int) -> List[Tuple[int, Tuple[int, ...]]]:
-    """(column, vertex positions) for every non-empty subset mask of K vertices."""
-    return [(m - 1, tuple(k for k in range(K) if m >> k & 1)) for m in range(1, 1 << K)]
-
-
-def _collect_faces(d_simplices: np.ndarray, values: np.ndarray, out: Dict[Tuple[int, ...], float]) -> None:
-    """Grid mode: spread the (S, 2^K-1) face values over the face keys.  A face shared by several
-    cells is computed once per coface from bit-identical sample points; the smallest value is
-    kept (it has seen the union of the cofaces' candidate balls)."""
-    K = d_simplices.shape[1]
-    by_size: Dict[int, List[Tuple[np.ndarray, np.ndarray]]] = {}
-    for col, pos in _face_columns(K):
-        by_size.setdefault(len(pos), []).append((d_simplices[:, list(pos)], values[:, col]))
-    for size, parts in by_size.items():
-        keys = np.concatenate([p[0] for p in parts], axis=0)
-        vals = np.concatenate([p[1] for p in parts], axis=0).astype(np.float64)
-        uniq, inv = np.unique(keys, axis=0, return_inverse=True)
-        best = np.full(len(uniq), np.inf)
-        np.minimum.at(best, inv.reshape(-1), vals)
-        out.update(zip(map(tuple, uniq.tolist()), best.tolist()))
+def _scatter_face_values(table: FaceTable, cell_values: np.ndarray, values: Dict[int, np.ndarray]) -> None:
+    """Grid mode: spread the (S, 2^K-1) per-cell face values over the unique faces.  Column
+    ``m-1`` of ``cell_values`` belongs to the face made of the vertex positions set in ``m``.  A
+    face shared by several cells is computed once per coface from bit-identical sample points;
+    the smallest value is kept (it has seen the union of the cofaces' candidate balls)."""
+    for k, combos in table.combos.items():
+        cols = [sum(1 << p for p in combo) - 1 for combo in combos]
+        best = np.full(len(table.faces[k]), np.inf)
+        np.minimum.at(best, table.cell_face[k].reshape(-1), cell_values[:, cols].astype(np.float64).reshape(-1))
+        values[k] = best
 
 
 def flood_complex(
@@ -241,46 +244,62 @@ def flood_complex(
     torch.cuda.set_device(device)
 
     lms32 = landmarks.detach().to(torch.float32)
-    stree = delaunay_simplex_tree(lms32.cpu().numpy())                     # host, as in the reference
-    simplices: List[List[Tuple[int, ...]]] = [[] for _ in range(max_dimension + 1)]
-    for simplex, _ in stree.get_simplices():
-        if len(simplex) <= max_dimension + 1:
-            simplices[len(simplex) - 1].append(tuple(simplex))
-
+    cells, gudhi_tree = delaunay_complex(lms32.cpu().numpy())               # host, as in the reference
+    K = cells.shape[1]
+    grid_mode = num_rand is None
+    max_dimension = min(max_dimension, K - 1)          # degenerate inputs have lower-dimensional cells
     cloud = PreparedCloud(points)
     shard = fdist.current_shard()
-    out_complex: Dict[Tuple[int, ...], float] = {}
-    for d in range(max_dimension + 1):
-        if num_rand is None and d < max_dimension:
-            continue
-        if len(simplices[d]) == 0:
-            continue
-        d_simplices_np = np.asarray(simplices[d], dtype=np.int64)
-        d_simplices = torch.as_tensor(d_simplices_np, device=device)
-        simplex_vertices = lms32[d_simplices]
-        if num_rand is None:
-            weights, _, _ = generate_grid(points_per_edge, max_dimension, device, torch.float32)
-        else:
-            weights = generate_uniform_weights(num_rand, d, device, torch.float32)
-        if shard is None:
-            values = covering_values(cloud, simplex_vertices, weights, grid_mode=num_rand is None)
-        else:
-            values = fdist.sharded_covering_values(
-                shard, simplex_vertices,
-                lambda v: covering_values(cloud, v, weights, grid_mode=num_rand is None),
-            )
-        values_np = values.cpu().numpy()
-        if num_rand is None:
-            _collect_faces(d_simplices_np, values_np, out_complex)
-        else:
-            out_complex.update(zip(simplices[d], values_np[:, 0].astype(np.float64).tolist()))
 
-    if isinstance(stree, SimplexTree):
-        stree.assign_many(list(out_complex.keys()), list(out_complex.values()))
-    else:  # pragma: no cover  (gudhi)
-        for simplex, value in out_complex.items():
-            stree.assign_filtration(simplex, value)
-    stree.make_filtration_non_decreasing()
+    def launch(d_simplices_np: np.ndarray, weights: torch.Tensor) -> torch.Tensor:
+        """Enqueue one dimension pass (asynchronous); returns the device tensor of values."""
+        simplex_vertices = lms32[torch.as_tensor(d_simplices_np, device=device)]
+        if shard is None:
+            return covering_values(cloud, simplex_vertices, weights, grid_mode=grid_mode)
+        return fdist.sharded_covering_values(
+            shard, simplex_vertices, lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode))
+
+    # Grid mode on full-dimensional cells needs nothing but the cells: enqueue the kernels first
+    # and build the face table on the host while the GPU works.
+    pending = None
+    if grid_mode and max_dimension == K - 1 and cells.shape[0] > 0:
+        pending = launch(cells, _grid_weights(points_per_edge, max_dimension, device))
+    table = FaceTable(cells, n_vertices=lms32.shape[0])
+    values = table.nan_values()           # NaN = not assigned (simplices above max_dimension)
+    if pending is not None:
+        _scatter_face_values(table, pending.cpu().numpy(), values)
+    else:
+        for d in range(max_dimension + 1):
+            if grid_mode and d < max_dimension:
+                continue
+            # grid mode evaluates the max_dimension-faces and reads all lower faces off the same
+            # samples; random mode evaluates every dimension on its own
+            sub = table if d + 1 == K else FaceTable(table.faces[d + 1], n_vertices=table.base)
+            if sub.cells.shape[0] == 0:
+                continue
+            if grid_mode:
+                weights = _grid_weights(points_per_edge, max_dimension, device)
+            else:
+                weights = generate_uniform_weights(num_rand, d, device, torch.float32)
+            host_values = launch(sub.cells, weights).cpu().numpy()
+            if grid_mode:
+                _scatter_face_values(sub, host_values, values)
+            else:
+                values[d + 1] = host_values[:, 0].astype(np.float64)
+
+    if gudhi_tree is not None:  # pragma: no cover  (gudhi is not in the build image)
+        stree = gudhi_tree
+        for k, faces in table.faces.items():
+            for simplex, value in zip(faces.tolist(), values[k].tolist()):
+                if value == value:
+                    stree.assign_filtration(simplex, value)
+        stree.make_filtration_non_decreasing()
+        if return_simplex_tree:
+            return stree
+        return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())
+
+    table.make_non_decreasing(values)
+    stree = SimplexTree.from_arrays(table.faces, values)
     if return_simplex_tree:
         return stree
-    return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())
+    return dict(stree._f)

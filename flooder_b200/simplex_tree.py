@@ -49,6 +49,74 @@ def faces_of_cells(cells: np.ndarray, k: int) -> np.ndarray:
     return np.unique(faces, axis=0)
 
 
+class FaceTable:
+    """All faces of a pure simplicial complex given by its top cells, as arrays.
+
+    For every face size k (1..K) it holds the unique faces as a lexicographically sorted
+    ``(F_k, k)`` array and, for every top cell, the ids of its faces in the order of
+    ``itertools.combinations(range(K), k)``.  Rows are packed into int64 keys (base = number of
+    vertices) when they fit, which turns ``np.unique`` / facet lookups into 1-D sorts; this is the
+    vectorised replacement of the reference's python loops over simplices
+    (``flooder/core.py:135-138, 258-263, 278-288``).
+    """
+
+    def __init__(self, cells: np.ndarray, n_vertices: Optional[int] = None) -> None:
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        self.cells = cells
+        self.K = K = cells.shape[1]
+        self.base = int(n_vertices if n_vertices is not None else (cells.max() + 1 if cells.size else 1))
+        self.combos = {k: list(itertools.combinations(range(K), k)) for k in range(1, K + 1)}
+        self.faces: Dict[int, np.ndarray] = {}
+        self.keys: Dict[int, Optional[np.ndarray]] = {}
+        self.cell_face: Dict[int, np.ndarray] = {}
+        for k in range(1, K + 1):
+            cols = np.asarray(self.combos[k], dtype=np.int64)
+            rows = cells[:, cols].reshape(-1, k)
+            uniq_rows, keys, inv = self._unique(rows)
+            self.faces[k] = uniq_rows
+            self.keys[k] = keys
+            self.cell_face[k] = inv.reshape(cells.shape[0], len(self.combos[k]))
+
+    def _packable(self, k: int) -> bool:
+        return k * np.log2(max(self.base, 2)) < 62.0
+
+    def _pack(self, rows: np.ndarray) -> np.ndarray:
+        key = rows[:, 0].copy()
+        for j in range(1, rows.shape[1]):
+            key = key * self.base + rows[:, j]
+        return key
+
+    def _unique(self, rows: np.ndarray):
+        k = rows.shape[1]
+        if self._packable(k):
+            keys, first, inv = np.unique(self._pack(rows), return_index=True, return_inverse=True)
+            return rows[first], keys, inv.reshape(-1)
+        uniq, inv = np.unique(rows, axis=0, return_inverse=True)
+        return uniq, None, inv.reshape(-1)
+
+    def lookup(self, rows: np.ndarray) -> np.ndarray:
+        """Ids of the given faces (all must exist) in ``faces[k]``."""
+        k = rows.shape[1]
+        if self.keys[k] is not None:
+            return np.searchsorted(self.keys[k], self._pack(rows))
+        table = {tuple(r): i for i, r in enumerate(self.faces[k].tolist())}
+        return np.fromiter((table[tuple(r)] for r in rows.tolist()), dtype=np.int64, count=len(rows))
+
+    def nan_values(self) -> Dict[int, np.ndarray]:
+        return {k: np.full(len(self.faces[k]), np.nan) for k in self.faces}
+
+    def make_non_decreasing(self, values: Dict[int, np.ndarray]) -> None:
+        """In place: every face is raised to the largest value among its facets, by increasing
+        size; NaN (unassigned) counts as minus infinity (np.fmax ignores NaN)."""
+        for k in range(2, self.K + 1):
+            f = self.faces[k]
+            best = np.full(len(f), np.nan)
+            for drop in range(k):
+                facet = np.delete(f, drop, axis=1)
+                best = np.fmax(best, values[k - 1][self.lookup(facet)])
+            values[k] = np.fmax(values[k], best)
+
+
 class SimplexTree:
     """Filtered simplicial complex keyed by ascending vertex tuples.
 
@@ -68,6 +136,13 @@ class SimplexTree:
         width = np.asarray(cells).shape[1]
         for k in range(1, width + 1):
             st._f.update(dict.fromkeys(map(tuple, faces_of_cells(cells, k).tolist()), nan))
+        return st
+
+    @classmethod
+    def from_arrays(cls, faces: Dict[int, np.ndarray], values: Dict[int, np.ndarray]) -> "SimplexTree":
+        st = cls()
+        for k in sorted(faces):
+            st._f.update(zip(map(tuple, faces[k].tolist()), values[k].tolist()))
         return st
 
     def insert(self, simplex: Iterable[int], filtration: float = 0.0) -> bool:
@@ -157,9 +232,15 @@ class SimplexTree:
         return {tuple(s): v for s, v in self.get_simplices()}
 
 
-def delaunay_simplex_tree(landmarks: np.ndarray):
-    """(tree, cells): gudhi objects when gudhi is installed, the stand-ins otherwise."""
+def delaunay_complex(landmarks: np.ndarray):
+    """Host Delaunay step.  Returns ``(cells, gudhi_tree_or_None)``: with gudhi installed the
+    triangulation and the container are gudhi's (as in the reference), otherwise Qhull's cells."""
     if HAS_GUDHI:  # pragma: no cover
         tree = _gudhi.DelaunayComplex(np.asarray(landmarks)).create_simplex_tree()
-        return tree
-    return SimplexTree.from_cells(delaunay_cells(landmarks))
+        width = landmarks.shape[1] + 1
+        cells = np.asarray([s for s, _ in tree.get_simplices() if len(s) == width], dtype=np.int64)
+        if cells.size == 0:  # degenerate input: fall back to the maximal simplices present
+            top = max(len(s) for s, _ in tree.get_simplices())
+            cells = np.asarray([s for s, _ in tree.get_simplices() if len(s) == top], dtype=np.int64)
+        return cells, tree
+    return delaunay_cells(landmarks), None

@@ -54,15 +54,17 @@ def install() -> None:
             sys.modules["fpsample"] = f
 
 
-def import_reference():
-    """Import the reference package from ``/root/reference`` with the stand-ins in place."""
+def import_reference(root: str = REFERENCE_ROOT):
+    """Import the reference package from ``root`` (``/root/reference`` in the authoring
+    container, or the pip-installed copy under ``baseline/_ref`` on the GPU box) with the
+    stand-ins in place."""
     import os
 
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "flooder")):
-        raise ImportError(f"{REFERENCE_ROOT} is not available on this machine")
+    if not os.path.isdir(os.path.join(root, "flooder")):
+        raise ImportError(f"{root} holds no reference package on this machine")
     install()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import flooder  # the reference package
 
     return flooder

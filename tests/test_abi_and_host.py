@@ -10,7 +10,7 @@ import torch
 
 import flooder_b200 as fb
 from flooder_b200 import _native, core
-from flooder_b200.simplex_tree import SimplexTree, delaunay_cells, faces_of_cells
+from flooder_b200.simplex_tree import FaceTable, SimplexTree, delaunay_cells, faces_of_cells
 from oracle import flood_oracle
 from oracle.simplex_tree import DictSimplexTree, delaunay_top_simplices
 from tests.helpers import load_golden, seed_all
@@ -104,15 +104,45 @@ def test_support_masks_select_reference_faces():
             np.testing.assert_array_equal(mine, rows[j].numpy())
 
 
-def test_collect_faces_min_over_cofaces():
+def test_scatter_face_values_min_over_cofaces():
     cells = np.array([[0, 1, 2], [1, 2, 3]])
     vals = np.arange(14, dtype=np.float32).reshape(2, 7)
-    out = {}
-    core._collect_faces(cells, vals, out)
+    table = FaceTable(cells, n_vertices=4)
+    values = table.nan_values()
+    core._scatter_face_values(table, vals, values)
+    out = {tuple(f): v for k in table.faces for f, v in zip(table.faces[k].tolist(), values[k].tolist())}
     assert out[(0, 1, 2)] == 6 and out[(1, 2, 3)] == 13
     assert out[(1, 2)] == min(vals[0, 0b110 - 1], vals[1, 0b011 - 1])
     assert out[(0,)] == vals[0, 0] and out[(3,)] == vals[1, 0b100 - 1]
     assert len(out) == 4 + 5 + 2
+
+
+@pytest.mark.parametrize("n_vertices", [40, 3_000_000_000])
+def test_face_table_matches_dict_tree(n_vertices):
+    """Array face table (packed int64 keys, and the unpackable fallback) == the dict tree,
+    including the monotone fix-up with unassigned (NaN) simplices."""
+    rng = np.random.default_rng(3)
+    pts = rng.random((40, 4))
+    cells = delaunay_cells(pts)
+    table = FaceTable(cells, n_vertices=n_vertices)
+    assert (table.keys[5] is None) == (n_vertices > 1e9)
+    ref = DictSimplexTree.from_top_simplices(cells)
+    keys = [tuple(s) for s, _ in ref.get_simplices()]
+    mine = [tuple(f) for k in sorted(table.faces) for f in table.faces[k].tolist()]
+    assert mine == keys
+    for k in table.faces:                       # cell -> face ids are consistent
+        cols = np.asarray(table.combos[k])
+        np.testing.assert_array_equal(table.faces[k][table.cell_face[k]], cells[:, cols])
+    values = table.nan_values()
+    for k in (1, 2, 4):                          # triangles (3) and cells (5) stay unassigned
+        values[k] = rng.random(len(table.faces[k]))
+        for f, v in zip(table.faces[k].tolist(), values[k].tolist()):
+            ref.assign_filtration(f, v)
+    table.make_non_decreasing(values)
+    ref.make_filtration_non_decreasing()
+    st = SimplexTree.from_arrays(table.faces, values)
+    for (s, f), (s2, f2) in zip(st.get_simplices(), ref.get_simplices()):
+        assert s == s2 and f == f2
 
 
 @pytest.mark.parametrize("name", ["virus", "coral", "lockwasher"])
