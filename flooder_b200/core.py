@@ -273,19 +273,18 @@ def flood_complex(
             if grid_mode and d < max_dimension:
                 continue
             # grid mode evaluates the max_dimension-faces and reads all lower faces off the same
-            # samples; random mode evaluates every dimension on its own
-            sub = table if d + 1 == K else FaceTable(table.faces[d + 1], n_vertices=table.base)
-            if sub.cells.shape[0] == 0:
+            # samples; random mode evaluates every dimension on its own.  Rows follow
+            # table.faces[d + 1] (sorted, unique), the order values[d + 1] is indexed in.
+            d_cells = table.faces[d + 1]
+            if d_cells.shape[0] == 0:
                 continue
             if grid_mode:
-                weights = _grid_weights(points_per_edge, max_dimension, device)
-            else:
-                weights = generate_uniform_weights(num_rand, d, device, torch.float32)
-            host_values = launch(sub.cells, weights).cpu().numpy()
-            if grid_mode:
+                sub = FaceTable(d_cells, n_vertices=table.base)
+                host_values = launch(d_cells, _grid_weights(points_per_edge, max_dimension, device)).cpu().numpy()
                 _scatter_face_values(sub, host_values, values)
             else:
-                values[d + 1] = host_values[:, 0].astype(np.float64)
+                weights = generate_uniform_weights(num_rand, d, device, torch.float32)
+                values[d + 1] = launch(d_cells, weights).cpu().numpy()[:, 0].astype(np.float64)
 
     if gudhi_tree is not None:  # pragma: no cover  (gudhi is not in the build image)
         stree = gudhi_tree

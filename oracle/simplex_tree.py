@@ -136,6 +136,8 @@ class DelaunayComplex:
     """Stand-in for ``gudhi.DelaunayComplex`` (reference call site ``core.py:130-132``)."""
 
     def __init__(self, points) -> None:
+        if hasattr(points, "detach"):  # torch tensor, possibly on a CUDA device (core.py:130)
+            points = points.detach().cpu().numpy()
         self._points = np.asarray(points, dtype=np.float64)
 
     def create_simplex_tree(self) -> DictSimplexTree:
