@@ -48,7 +48,7 @@ WORKLOADS = {
     "torus_10k_100": ("torus", 10_000, 100, 3, 30),
     "gauss_10m_5k": ("gauss", 10_000_000, 5000, 3, 30),
 }
-KERNELS_PER_STEP = 12  # cloud build 6, balls 1, covering 4 (fill, plan, scan, eval), face max 1
+KERNELS_PER_STEP = 12  # cloud build 6, balls 1, covering 4 (fill, plan, scan, eval), face max 1 (+1 plan when sharded)
 SLOTS_PER_EVAL = {2: 5, 3: 7, 4: 9, 5: 11, 6: 13}
 
 
@@ -325,22 +325,26 @@ def run_cuda(args):
     weights, _, _ = fb.generate_grid(ppe, dim, dev)
     support = _support_masks(weights)
     R, K = weights.shape
-    if world > 1:
-        parts = fdist.partition(fdist.cost_proxy(verts_all), world)
-        mine = parts[rank]
-        shard = fdist.Shard(rank, world)
-    else:
-        parts, mine, shard = None, None, None
-    verts = verts_all if mine is None else verts_all[mine].contiguous()
+    shard = fdist.Shard(rank, world) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def device_step():
+        """The device path of one flood_complex call (what flooder_b200.core enqueues)."""
         ws = ext.cloud_build(pts, 0)
-        c, r = ext.bounding_balls(verts)
+        c_all, r_all = ext.bounding_balls(verts_all)
+        if shard is not None:          # balance by the candidate-stream lengths, largest first
+            cost = ext.covering_plan(ws, n, dim, c_all, r_all).to(torch.float32)
+            parts = fdist.partition(cost, world)
+            mine = parts[rank]
+        else:
+            parts, mine = None, torch.argsort(r_all, descending=True)
+        verts, c, r = verts_all[mine].contiguous(), c_all[mine].contiguous(), r_all[mine].contiguous()
         md2, cnt, ev = ext.covering_radius(ws, n, dim, verts, weights, None, c, r)
         vals = ext.face_max(md2, support, K)
         if shard is not None:
             vals = fdist.gather_rows(vals, parts, shard)
+        else:
+            vals = torch.empty_like(vals).index_copy_(0, mine, vals)
         return vals, ev
 
     def barrier():
@@ -447,7 +451,7 @@ def run_cuda(args):
                     "d2h_bytes_per_step": int((S_total * (2 ** K - 1) * 4 + host_lms_bytes) * world),
                     "flood_complex_wall_s": e2e_s, "steps": e2e_steps,
                     "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
-            "gpu_launches": KERNELS_PER_STEP * args.steps * world,
+            "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps * world,
             "roofline": roofline,
             "clocks": clock_info,
             "timed_region_wall_s": wall_s,

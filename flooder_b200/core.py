@@ -176,12 +176,27 @@ def covering_values(
     w = weights.to(torch.float32).contiguous()
     K = verts.shape[1]
     centers, radii = ext.bounding_balls(verts)
+    # Largest balls first: the kernel's work queue follows the simplex order, so the big items
+    # are dealt out early and the small ones fill the tail of the launch.
+    order = None
+    if samples is None and not return_details and verts.shape[0] > 1:
+        order = torch.argsort(radii, descending=True)
+        verts, centers, radii = verts[order].contiguous(), centers[order].contiguous(), radii[order].contiguous()
     min_d2, counts, evals = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples, centers, radii)
     support = _support_masks(w) if grid_mode else None
     values = ext.face_max(min_d2, support, K)
+    if order is not None:
+        values = torch.empty_like(values).index_copy_(0, order, values)
     if return_details:
         return values, dict(min_dist2=min_d2, cand_count=counts, evals=evals, centers=centers, radii=radii)
     return values
+
+
+def covering_cost(cloud: PreparedCloud, simplex_vertices: torch.Tensor) -> torch.Tensor:
+    """Per-simplex cost estimate (length of the candidate stream, ``flood_covering_plan_f32``)."""
+    ext = _native.ext()
+    centers, radii = ext.bounding_balls(simplex_vertices.to(torch.float32).contiguous())
+    return ext.covering_plan(cloud.workspace, cloud.n, cloud.d, centers, radii).to(torch.float32)
 
 
 def _scatter_face_values(table: FaceTable, cell_values: np.ndarray, values: Dict[int, np.ndarray]) -> None:
@@ -257,7 +272,8 @@ def flood_complex(
         if shard is None:
             return covering_values(cloud, simplex_vertices, weights, grid_mode=grid_mode)
         return fdist.sharded_covering_values(
-            shard, simplex_vertices, lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode))
+            shard, simplex_vertices, lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode),
+            cost=covering_cost(cloud, simplex_vertices))
 
     # Grid mode on full-dimensional cells needs nothing but the cells: enqueue the kernels first
     # and build the face table on the host while the GPU works.

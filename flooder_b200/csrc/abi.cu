@@ -154,6 +154,11 @@ int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, con
                            (cudaStream_t)stream);
 }
 
+int flood_covering_plan_f32(const void *cloud_workspace, int64_t n, int d, const float *centers,
+                            const float *radii, int64_t S, int32_t *out_tested, void *stream) {
+    return covering_plan(cloud_workspace, n, d, centers, radii, S, out_tested, (cudaStream_t)stream);
+}
+
 int flood_face_max_f32(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K,
                        float *out, void *stream) {
     return face_max(min_dist2, S, R, support, K, out, (cudaStream_t)stream);

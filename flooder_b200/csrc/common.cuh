@@ -117,6 +117,8 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
                     const float *weights, int64_t R, const float *samples, const float *centers,
                     const float *radii, float *out_min_dist2, int64_t *out_cand_count,
                     unsigned long long *out_evals, void *ws, size_t ws_bytes, cudaStream_t st);
+int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, const float *radii,
+                  int64_t S, int32_t *out_tested, cudaStream_t st);
 int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, float *out,
              cudaStream_t st);
 size_t fps_workspace_bytes(int64_t n, int d, int64_t n_lms);

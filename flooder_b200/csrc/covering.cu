@@ -124,7 +124,7 @@ __global__ void cover_plan_kernel(CoverParams P, int d) {
     if (lane == 0) {
         P.tested[warp] = (int)total;
         // number of chunks, stored in place and scanned by cover_scan_kernel
-        P.item_base[warp] = (total + P.chunk - 1) / P.chunk;
+        if (P.item_base) P.item_base[warp] = (total + P.chunk - 1) / P.chunk;
     }
 }
 
@@ -520,6 +520,32 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
 }
 
 }  // namespace
+
+// cost estimate per simplex: length of its candidate stream (points in the cell rows its ball
+// touches); used by the host to balance simplices over GPUs
+int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, const float *radii,
+                  int64_t S, int32_t *out_tested, cudaStream_t st) {
+    if (S == 0) return FLOOD_OK;
+    if (!cloud_ws || !centers || !radii || !out_tested || S < 0 || n < 1 || d < 2 || d > FLOOD_MAX_DIM)
+        return set_error(FLOOD_E_INVALID, "covering_plan: bad arguments (S=%lld n=%lld d=%d)", (long long)S,
+                         (long long)n, d);
+    const CloudLayout C = cloud_layout(n, d);
+    const char *cbase = static_cast<const char *>(cloud_ws);
+    CoverParams P = {};
+    P.gp = reinterpret_cast<const GridParams *>(cbase + C.off_grid);
+    P.cell_start = reinterpret_cast<const int *>(cbase + C.off_cell_start);
+    P.centers = centers;
+    P.radii = radii;
+    P.tested = out_tested;
+    P.item_base = nullptr;
+    P.S = S;
+    P.chunk = 1;
+    const int threads = 128;
+    const long long blocks = (S * 32 + threads - 1) / threads;
+    cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
+    FLOOD_LAUNCH_CHECK("cover_plan_kernel");
+    return FLOOD_OK;
+}
 
 size_t covering_workspace_bytes(int64_t S, int64_t R, int d) {
     (void)R; (void)d;

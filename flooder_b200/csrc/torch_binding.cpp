@@ -109,6 +109,19 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> covering_radius(
     return {out, counts, evals};
 }
 
+torch::Tensor covering_plan(const torch::Tensor &cloud_ws, int64_t n, int64_t d, const torch::Tensor &centers,
+                            const torch::Tensor &radii) {
+    need_cuda_f32(centers, "centers");
+    need_cuda_f32(radii, "radii");
+    TORCH_CHECK(centers.dim() == 2 && centers.size(1) == d && radii.numel() == centers.size(0), "bad ball shapes");
+    const c10::cuda::CUDAGuard guard(centers.device());
+    auto out = torch::empty({centers.size(0)}, centers.options().dtype(torch::kInt32));
+    check(flood_covering_plan_f32(cloud_ws.data_ptr(), n, (int)d, centers.data_ptr<float>(), radii.data_ptr<float>(),
+                                  centers.size(0), out.data_ptr<int32_t>(), current_stream(centers)),
+          "flood_covering_plan_f32");
+    return out;
+}
+
 torch::Tensor face_max(const torch::Tensor &min_dist2, const c10::optional<torch::Tensor> &support, int64_t K) {
     need_cuda_f32(min_dist2, "min_dist2");
     TORCH_CHECK(min_dist2.dim() == 2, "min_dist2 must be (S, R)");
@@ -149,6 +162,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("bounding_balls", &bounding_balls);
     m.def("covering_radius", &covering_radius);
     m.def("face_max", &face_max);
+    m.def("covering_plan", &covering_plan);
     m.def("set_option", &set_option);
     m.def("kernel_ms", &kernel_ms);
 }

@@ -39,13 +39,24 @@ def current_shard() -> Optional[Shard]:
 
 
 def partition(cost: torch.Tensor, world: int) -> List[torch.Tensor]:
-    """Deal simplices to ranks round-robin in order of decreasing cost proxy.
-
-    The heavy tail (a few simplices whose ball swallows most of the cloud) is spread first, and
-    every rank receives the same cost distribution.  Deterministic: ties are broken by index.
+    """Deal simplices to ranks in order of decreasing cost, in serpentine order
+    (0..w-1, w-1..0, ...), so that the heavy tail (a few simplices whose ball swallows most of the
+    cloud) is spread first and the per-rank cost sums stay within a fraction of the smallest
+    items.  Every rank's share is itself sorted by decreasing cost (big work items first, small
+    ones fill the tail).  Deterministic: ties are broken by index.
     Returns one int64 index tensor per rank (on ``cost.device``)."""
+    n = int(cost.numel())
     order = torch.argsort(cost, descending=True, stable=True)
-    return [order[r::world].contiguous() for r in range(world)]
+    pos = torch.arange(n, device=order.device)
+    lap, col = pos // world, pos % world
+    owner = torch.where(lap % 2 == 0, col, world - 1 - col)
+    # share sizes are known on the host, so no device->host synchronisation is needed
+    laps, rem = divmod(n, world)
+    sizes = [laps] * world
+    for c in range(rem):
+        sizes[c if laps % 2 == 0 else world - 1 - c] += 1
+    grouped = order[torch.argsort(owner, stable=True)]
+    return [p.contiguous() for p in torch.split(grouped, sizes)]
 
 
 def cost_proxy(simplex_vertices: torch.Tensor) -> torch.Tensor:
@@ -78,9 +89,12 @@ def sharded_covering_values(
     shard: Shard,
     simplex_vertices: torch.Tensor,
     compute: Callable[[torch.Tensor], torch.Tensor],
+    cost: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Evaluate ``compute`` on this rank's share of the simplices and all-gather the rows."""
-    parts = partition(cost_proxy(simplex_vertices), shard.world)
+    """Evaluate ``compute`` on this rank's share of the simplices and all-gather the rows.
+    ``cost`` (one value per simplex, identical on every rank) drives the partition; without it
+    the longest edge is used."""
+    parts = partition(cost_proxy(simplex_vertices) if cost is None else cost, shard.world)
     mine = parts[shard.rank]
     local = compute(simplex_vertices[mine].contiguous())
     return gather_rows(local, parts, shard)

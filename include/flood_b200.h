@@ -104,6 +104,12 @@ int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, con
                               unsigned long long *out_evals, void *workspace,
                               size_t workspace_bytes, void *stream);
 
+/* Cost estimate: out_tested[s] = number of cloud points in the cell rows touched by ball s (an
+ * upper bound of cand_count[s], obtained from the cell table alone).  New with the multi-GPU
+ * sharding (the reference is single-GPU): the host balances simplices over ranks with it. */
+int flood_covering_plan_f32(const void *cloud_workspace, int64_t n, int d, const float *centers,
+                            const float *radii, int64_t S, int32_t *out_tested, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Face maxima.  support: [R] int32 bit masks (bit k set <=> weights[r, k] != 0) or NULL.
  *   support != NULL (grid mode):  out[s, m-1] = sqrt(max_{r : support[r] subset of m} min_dist2[s, r])
