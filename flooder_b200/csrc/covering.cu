@@ -25,8 +25,6 @@
 namespace flood {
 namespace {
 
-// candidate records per shared-memory tile (static shared memory is capped at 48 KB)
-__host__ __device__ constexpr int tile_cap(int d) { return d <= 4 ? 2048 : 1024; }
 constexpr int kUnroll = 4;       // candidates per inner-loop trip
 
 struct CoverParams {
@@ -47,6 +45,9 @@ struct CoverParams {
     long long S, R;
     int K;
     int nsb;                 // sample blocks per simplex
+    int groups;              // ceil(R / 32) sample groups per simplex
+    int groups_per_block;    // groups handled by one CTA pass (sample block)
+    int tile_cap;            // candidate records per shared-memory tile
     int chunk;               // target tested points per chunk
 };
 
@@ -241,26 +242,72 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &
 // ---------------------------------------------------------------------------------------------
 // the persistent evaluation kernel
 // ---------------------------------------------------------------------------------------------
-template <int D, int T, int MAXW, int MINB>
-__global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
-    using RecT = typename Rec<D>::type;
-    constexpr int NTMAX = MAXW * 32;
+constexpr int kMaxT = 8;       // sample groups (32 samples each) per warp
+constexpr int kMaxWarps = 20;  // warps per CTA
 
-    constexpr int kTileCap = tile_cap(D);
-    __shared__ RecT tile[kTileCap + kUnroll];
-    __shared__ int run_start[NTMAX];
-    __shared__ int run_pos[NTMAX + 1];
+// Sweep of a padded tile by one warp that holds NT_ sample groups in registers: the hot loop.
+// Two samples share one packed FP32x2 instruction (FADD2 / FMUL2 / FFMA2 take the candidate
+// coordinate as a broadcast scalar operand), two candidates share one 3-input FMNMX3: per pair of
+// samples and pair of candidates that is 2 x (D FADD2 + FMUL2 + (D-1) FFMA2) + 2 FMNMX3 issue slots
+// for four evaluations.  An odd group is handled with the scalar form.  Each lane result is the
+// same IEEE operation as the scalar form (x - p, round; *, round; fma, round), so the minima are
+// bit-identical to a scalar evaluation.
+template <int D, int NT_>
+__device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restrict__ tile, int npad,
+                                           const float (&x)[kMaxT][D], float (&m)[kMaxT]) {
+#pragma unroll 1
+    for (int j = 0; j < npad; j += kUnroll) {
+        float p[kUnroll][D];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u += 2) {
+#pragma unroll
+            for (int t = 0; t + 1 < NT_; t += 2) {
+                float2 acc[2];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    float2 df = __fadd2_rn(make_float2(x[t][0], x[t + 1][0]),
+                                           make_float2(-p[u + v][0], -p[u + v][0]));
+                    acc[v] = __fmul2_rn(df, df);
+#pragma unroll
+                    for (int a = 1; a < D; ++a) {
+                        df = __fadd2_rn(make_float2(x[t][a], x[t + 1][a]),
+                                        make_float2(-p[u + v][a], -p[u + v][a]));
+                        acc[v] = __ffma2_rn(df, df, acc[v]);
+                    }
+                }
+                m[t] = fmin3(m[t], acc[0].x, acc[1].x);
+                m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
+            }
+            if (NT_ & 1) {
+                constexpr int t = NT_ - 1;
+                m[t] = fmin3(m[t], dist2<D>(x[t], p[u]), dist2<D>(x[t], p[u + 1]));
+            }
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const CoverParams P) {
+    using RecT = typename Rec<D>::type;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x;
+    const int tile_cap = P.tile_cap;
+    RecT *tile = reinterpret_cast<RecT *>(smem_raw);
+    int *run_start = reinterpret_cast<int *>(smem_raw + (size_t)(tile_cap + kUnroll) * sizeof(RecT));
+    int *run_pos = run_start + NT;
     __shared__ int warp_sums[32];
     __shared__ int s_fill;
     __shared__ long long s_item[3];  // simplex, chunk, sample block (-1 = queue drained)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NT = blockDim.x;
+    const int W = NT >> 5;
     const GridParams gp = *P.gp;
     const RecT *__restrict__ points = reinterpret_cast<const RecT *>(P.points);
     const long long total_chunks = P.item_base[P.S];
     const unsigned long long total_items = (unsigned long long)total_chunks * (unsigned)P.nsb;
-    const int SB = NT * T;
 
     if (tid == 0) s_fill = 0;
 
@@ -301,13 +348,21 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
         const int win_lo = (int)(chunk_j * tested / nch);
         const int win_hi = (int)((chunk_j + 1) * tested / nch);
 
-        // ---- this thread's sample points -----------------------------------------------------
-        float x[T][D], m[T];
+        // ---- this warp's sample groups ---------------------------------------------------------
+        // The sample block's groups (32 consecutive samples each) are dealt to the warps as evenly
+        // as possible; consecutive warps sit on different SM sub-partitions, so the sub-partition
+        // loads differ by at most one group.
+        const int blk_g0 = sb * P.groups_per_block;
+        const int blk_groups = min(P.groups_per_block, P.groups - blk_g0);
+        const int g_base = blk_groups / W, g_rem = blk_groups % W;
+        const int nt = g_base + (warp < g_rem ? 1 : 0);
+        const int g0 = blk_g0 + warp * g_base + min(warp, g_rem);
+        float x[kMaxT][D], m[kMaxT];
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const long long r = (long long)sb * SB + warp * (32 * T) + t * 32 + lane;
+        for (int t = 0; t < kMaxT; ++t) {
+            const long long r = (long long)(g0 + t) * 32 + lane;
             m[t] = INFINITY;
-            if (r < P.R) {
+            if (t < nt && r < P.R) {
                 if (P.samples) {
 #pragma unroll
                     for (int a = 0; a < D; ++a) x[t][a] = __ldg(P.samples + (s * P.R + r) * D + a);
@@ -331,42 +386,20 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             }
         }
 
-        // sweep of the shared tile by all warps: the hot loop.  Two samples share one packed
-        // FP32x2 instruction (FADD2 / FMUL2 / FFMA2 take the candidate coordinate as a broadcast
-        // scalar operand), two candidates share one 3-input FMNMX3: per pair of samples and pair
-        // of candidates that is 2 x (D FADD2 + FMUL2 + (D-1) FFMA2) + 2 FMNMX3 issue slots for four
-        // evaluations.  Each lane result is the same IEEE operation as the scalar form
-        // (x - p, round; * , round; fma, round), so the minima are bit-identical.
         auto sweep = [&](int n) {
             const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
             if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
             __syncthreads();
-#pragma unroll 1
-            for (int j = 0; j < npad; j += kUnroll) {
-                float p[kUnroll][D];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
-#pragma unroll
-                for (int u = 0; u < kUnroll; u += 2) {
-#pragma unroll
-                    for (int t = 0; t < T; t += 2) {
-                        float2 acc[2];
-#pragma unroll
-                        for (int v = 0; v < 2; ++v) {
-                            float2 df = __fadd2_rn(make_float2(x[t][0], x[t + 1][0]),
-                                                   make_float2(-p[u + v][0], -p[u + v][0]));
-                            acc[v] = __fmul2_rn(df, df);
-#pragma unroll
-                            for (int a = 1; a < D; ++a) {
-                                df = __fadd2_rn(make_float2(x[t][a], x[t + 1][a]),
-                                                make_float2(-p[u + v][a], -p[u + v][a]));
-                                acc[v] = __ffma2_rn(df, df, acc[v]);
-                            }
-                        }
-                        m[t] = fmin3(m[t], acc[0].x, acc[1].x);
-                        m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
-                    }
-                }
+            switch (nt) {  // warp-uniform
+                case 1: sweep_tile<D, 1>(tile, npad, x, m); break;
+                case 2: sweep_tile<D, 2>(tile, npad, x, m); break;
+                case 3: sweep_tile<D, 3>(tile, npad, x, m); break;
+                case 4: sweep_tile<D, 4>(tile, npad, x, m); break;
+                case 5: sweep_tile<D, 5>(tile, npad, x, m); break;
+                case 6: sweep_tile<D, 6>(tile, npad, x, m); break;
+                case 7: sweep_tile<D, 7>(tile, npad, x, m); break;
+                case 8: sweep_tile<D, 8>(tile, npad, x, m); break;
+                default: break;
             }
             __syncthreads();
             if (tid == 0) s_fill = 0;
@@ -398,7 +431,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             __syncthreads();
 
             for (int base = 0; base < total2; base += NT) {
-                if (fill + NT > kTileCap) {
+                if (fill + NT > tile_cap) {
                     accepted += fill;
                     sweep(fill);
                     __syncthreads();
@@ -443,9 +476,9 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
 
         // ---- merge -----------------------------------------------------------------------------
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const long long r = (long long)sb * SB + warp * (32 * T) + t * 32 + lane;
-            if (r < P.R && m[t] < INFINITY)
+        for (int t = 0; t < kMaxT; ++t) {
+            const long long r = (long long)(g0 + t) * 32 + lane;
+            if (t < nt && r < P.R && m[t] < INFINITY)
                 atomicMin(reinterpret_cast<unsigned *>(P.out + s * P.R + r), __float_as_uint(m[t]));
         }
         if (tid == 0 && sb == 0 && accepted > 0) {
@@ -476,47 +509,46 @@ CoverLayout cover_layout(int64_t S) {
     return L;
 }
 
-template <int D, int T, int MAXW, int MINB>
-int launch_eval(const CoverParams &P, int nwarps, cudaStream_t st) {
-    auto kern = cover_eval_kernel<D, T, MAXW, MINB>;
+template <int D>
+int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
+    using RecT = typename Rec<D>::type;
+    auto kern = cover_eval_kernel<D>;
+    // Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
+    // sub-partition), at most kMaxT groups per warp; more than kMaxWarps * kMaxT groups are split
+    // into equal sample blocks.
+    const int G = (int)((R + 31) / 32);
+    auto warps_for = [](int groups) {
+        if (groups < 4) return groups < 1 ? 1 : groups;
+        int w = (groups + kMaxT - 1) / kMaxT;
+        w = (w + 3) / 4 * 4;
+        return w > kMaxWarps ? kMaxWarps : w;
+    };
+    int forced = get_option("warps", 0);
+    if (forced < 0 || forced > kMaxWarps) forced = 0;
+    int W = forced ? forced : warps_for(G);
+    P.nsb = (G + W * kMaxT - 1) / (W * kMaxT);
+    P.groups = G;
+    P.groups_per_block = (G + P.nsb - 1) / P.nsb;
+    if (!forced) W = warps_for(P.groups_per_block);
+    const int NT = W * 32;
+    int cap = NT >= 512 ? 2048 : (4 * NT < 512 ? 512 : 4 * NT);
+    const int forced_cap = get_option("tile_cap", 0);
+    if (forced_cap >= NT + kUnroll) cap = forced_cap / kUnroll * kUnroll;
+    P.tile_cap = cap;
+    const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int);
+    FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    FLOOD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, 0));
+    FLOOD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return set_error(FLOOD_E_CUDA, "cover_eval_kernel does not fit on an SM");
-    const int cap = get_option("ctas_per_sm", 0);
-    if (cap > 0 && per_sm > cap) per_sm = cap;
+    const int limit = get_option("ctas_per_sm", 0);
+    if (limit > 0 && per_sm > limit) per_sm = limit;
     const int grid = device_sm_count() * per_sm;
     const bool timed = get_option("time_kernels", 0) != 0;
     if (timed) kernel_timer_start("cover_eval", st);
-    kern<<<grid, nwarps * 32, 0, st>>>(P);
+    kern<<<grid, NT, smem, st>>>(P);
     if (timed) kernel_timer_stop("cover_eval", st);
     FLOOD_LAUNCH_CHECK("cover_eval_kernel");
     return FLOOD_OK;
-}
-
-template <int D>
-int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
-    // T = samples per thread, MAXW = warps per CTA.  Wide CTAs (20 warps, one per SM) cover the
-    // reference default R = 4960 (3-D, 30 points per edge) in one sample block.
-    const int mode = get_option("eval_mode", 0);
-    if (mode == 1) {  // 2 CTAs per SM, 10 warps each
-        constexpr int T = 8, MAXW = 10;
-        int nwarps = (int)((R + 32 * T - 1) / (32 * T));
-        if (nwarps > MAXW) nwarps = MAXW;
-        P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
-        return launch_eval<D, T, MAXW, 2>(P, nwarps, st);
-    }
-    if (R <= 32 * 4 * 8) {  // small sample sets: fewer samples per thread, more warps
-        constexpr int T = 4, MAXW = 8;
-        int nwarps = (int)((R + 32 * T - 1) / (32 * T));
-        if (nwarps > MAXW) nwarps = MAXW;
-        P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
-        return launch_eval<D, T, MAXW, 4>(P, nwarps, st);
-    }
-    constexpr int T = 8, MAXW = 20;
-    int nwarps = (int)((R + 32 * T - 1) / (32 * T));
-    if (nwarps > MAXW) nwarps = MAXW;
-    P.nsb = (int)((R + (int64_t)nwarps * 32 * T - 1) / ((int64_t)nwarps * 32 * T));
-    return launch_eval<D, T, MAXW, 1>(P, nwarps, st);
 }
 
 }  // namespace

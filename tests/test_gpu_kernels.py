@@ -125,7 +125,9 @@ def _check_against_bruteforce(pts, verts, weights, md2, cnt, ev, c, r, samples=N
 @pytest.mark.parametrize("kind,n,d,S,ppe", [
     ("torus", 5000, 3, 60, 8), ("gauss", 20000, 3, 40, 12), ("uniform", 3000, 2, 50, 20),
     ("uniform", 4000, 4, 30, 5), ("uniform", 3000, 5, 20, 4), ("uniform", 2500, 6, 12, 3),
-    ("gauss", 777, 3, 9, 30),
+    ("gauss", 777, 3, 9, 30), ("torus", 4000, 3, 20, 20), ("uniform", 3000, 2, 10, 130),
+    ("uniform", 2000, 3, 10, 2), ("uniform", 2000, 5, 10, 6), ("uniform", 2000, 6, 10, 4),
+    ("uniform", 1500, 7, 6, 3), ("uniform", 1500, 8, 6, 2),
 ])
 def test_covering_bruteforce(ext, kind, n, d, S, ppe):
     pts = _cloud(kind, n, d, seed=n)
@@ -141,11 +143,13 @@ def test_covering_bruteforce(ext, kind, n, d, S, ppe):
     _check_against_bruteforce(pts, verts, w, md2, cnt, ev, c, r)
 
 
-@pytest.mark.parametrize("option,value", [("chunk", 256), ("eval_mode", 1), ("points_per_cell", 1),
-                                          ("points_per_cell", 64)])
+@pytest.mark.parametrize("option,value", [("chunk", 256), ("warps", 8), ("warps", 3), ("warps", 13),
+                                          ("tile_cap", 700), ("ctas_per_sm", 1),
+                                          ("points_per_cell", 1), ("points_per_cell", 64)])
 def test_covering_options(ext, option, value):
-    """Chunk splitting (atomicMin merge), the 2-CTA/SM configuration and extreme cell sizes give
-    the same bits."""
+    """Chunk splitting (atomicMin merge), other CTA shapes (several sample blocks, uneven
+    groups per warp, odd group counts -> scalar leftover path), small tiles and extreme cell
+    sizes give the same bits."""
     pts = _cloud("torus", 30000, 3, seed=11)
     g = torch.Generator().manual_seed(5)
     lms = pts[torch.randperm(30000, generator=g)[:40]]
