@@ -404,6 +404,13 @@ def run_cuda(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = e2e_t.item()
     n_simplices = len(res)
+    # untimed diagnostic pass: per-stage seconds with a device sync after every stage
+    from flooder_b200 import core as fcore
+
+    fcore.PROFILE_STAGES = True
+    fb.flood_complex(host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)
+    fcore.PROFILE_STAGES = False
+    stage_seconds = {k: round(v, 5) for k, v in fcore.last_stage_seconds.items()}
 
     if rank == 0:
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -450,6 +457,7 @@ def run_cuda(args):
                     "h2d_bytes_per_step": int(n * dim * 4 * world),
                     "d2h_bytes_per_step": int((S_total * (2 ** K - 1) * 4 + host_lms_bytes) * world),
                     "flood_complex_wall_s": e2e_s, "steps": e2e_steps,
+                    "stage_seconds_serialised": stage_seconds,
                     "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
             "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps * world,
             "roofline": roofline,

@@ -59,6 +59,7 @@ def cdll() -> ctypes.CDLL:
         lib.flood_fps_workspace_bytes.argtypes = [c_i64, c_int, c_i64]
         lib.flood_fps_workspace_bytes.restype = c_sz
         lib.flood_fps_f32.argtypes = [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]
+        lib.flood_fps_grid_f32.argtypes = [c_vp, c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]
         lib.flood_cloud_workspace_bytes.argtypes = [c_i64, c_int]
         lib.flood_cloud_workspace_bytes.restype = c_sz
         lib.flood_cloud_build_f32.argtypes = [c_vp, c_i64, c_int, c_int, c_vp, c_sz, c_vp]
@@ -70,7 +71,7 @@ def cdll() -> ctypes.CDLL:
         lib.flood_covering_plan_f32.argtypes = [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]
         lib.flood_face_max_f32.argtypes = [c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]
         lib.flood_set_option.argtypes = [ctypes.c_char_p, c_int]
-        for fn in ("flood_device_info", "flood_fps_f32", "flood_cloud_build_f32", "flood_bounding_balls_f32",
+        for fn in ("flood_device_info", "flood_fps_f32", "flood_fps_grid_f32", "flood_cloud_build_f32", "flood_bounding_balls_f32",
                    "flood_covering_radius_f32", "flood_covering_plan_f32", "flood_face_max_f32", "flood_set_option"):
             getattr(lib, fn).restype = c_int
         _lib = lib
@@ -79,7 +80,7 @@ def cdll() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "flood_abi_version", "flood_last_error", "flood_device_info", "flood_set_option", "flood_kernel_ms",
-    "flood_fps_workspace_bytes", "flood_fps_f32",
+    "flood_fps_workspace_bytes", "flood_fps_f32", "flood_fps_grid_f32",
     "flood_cloud_workspace_bytes", "flood_cloud_build_f32",
     "flood_bounding_balls_f32",
     "flood_covering_workspace_bytes", "flood_covering_radius_f32", "flood_covering_plan_f32",

@@ -25,6 +25,32 @@ from .simplex_tree import FaceTable, SimplexTree, delaunay_complex
 
 _SUPPORTED_DTYPES = (torch.float32, torch.float64)
 
+# Optional stage timing of flood_complex (diagnostics; adds a device synchronisation per stage and
+# therefore removes the host/device overlap -- never enabled inside a timed benchmark region).
+PROFILE_STAGES = os.environ.get("FLOODER_B200_PROFILE", "0") == "1"
+last_stage_seconds: Dict[str, float] = {}
+
+
+class _Stage:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE_STAGES:
+            import time
+
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_STAGES:
+            import time
+
+            torch.cuda.synchronize()
+            last_stage_seconds[self.name] = last_stage_seconds.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
+
 
 # ----------------------------------------------------------------------------------------------
 # sample-point generators (host, tiny) -- same weights as the reference
@@ -107,11 +133,33 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         )
 
 
-def fps_indices(points: torch.Tensor, n_lms: int, start_idx: int = 0) -> torch.Tensor:
-    """Indices chosen by exact farthest-point sampling, int64 on ``points.device``."""
+def _fps_register_capacity(dim: int) -> int:
+    """Clouds up to this size stay register-resident in the brute-force FPS kernel (148 SMs x 1024
+    threads x 8 points for D <= 4, x 4 points above); measured on B200 it then needs ~4 us per
+    landmark, which the bucketed kernel only beats on larger clouds."""
+    return 148 * 1024 * (8 if dim <= 4 else 4)
+
+
+
+def fps_indices(points: torch.Tensor, n_lms: int, start_idx: int = 0, method: str = "auto",
+                cloud: Optional["PreparedCloud"] = None) -> torch.Tensor:
+    """Indices chosen by exact farthest-point sampling, int64 on ``points.device``.
+
+    ``method``: ``"brute"`` = every point every iteration (``flood_fps_f32``), ``"grid"`` = bucketed
+    on the cell grid of a prepared cloud (``flood_fps_grid_f32``), ``"auto"`` picks by size.  Both
+    return the same indices bit for bit."""
     _require_cuda(points, "points")
     pts32 = points.detach().to(torch.float32).contiguous()
-    return _native.ext().fps(pts32, int(n_lms), int(start_idx))
+    if method == "auto":
+        n, dim = pts32.shape
+        method = "grid" if (dim >= 2 and n > _fps_register_capacity(dim)) else "brute"
+    if method == "brute":
+        return _native.ext().fps(pts32, int(n_lms), int(start_idx))
+    if method != "grid":
+        raise ValueError(f"unknown FPS method {method!r}")
+    if cloud is None:
+        cloud = PreparedCloud(pts32)
+    return _native.ext().fps_grid(cloud.workspace, pts32, int(n_lms), int(start_idx))
 
 
 def generate_landmarks(
@@ -119,6 +167,8 @@ def generate_landmarks(
     n_lms: int,
     fps_h: Union[None, int] = None,
     start_idx: Union[int, None] = None,
+    *,
+    _cloud: Optional["PreparedCloud"] = None,
 ) -> torch.Tensor:
     """Selects landmarks using farthest-point sampling.
 
@@ -140,7 +190,7 @@ def generate_landmarks(
         if not torch.cuda.is_available():
             _require_cuda(points, "points")
         dev_points = points.cuda()
-    index_set = fps_indices(dev_points, n_lms, start_idx).to(points.device)
+    index_set = fps_indices(dev_points, n_lms, start_idx, cloud=_cloud).to(points.device)
     return points[index_set]
 
 
@@ -240,8 +290,16 @@ def flood_complex(
     del batch_size, use_triton
     if max_dimension is None:
         max_dimension = points.shape[1]
+    if PROFILE_STAGES:
+        last_stage_seconds.clear()
+    cloud = None
     if isinstance(landmarks, Integral):
-        landmarks = generate_landmarks(points, min(landmarks, points.shape[0]), fps_h, start_idx=start_idx)
+        if points.device.type == "cuda" and points.dtype in _SUPPORTED_DTYPES:
+            with _Stage("cloud_build"):
+                cloud = PreparedCloud(points)      # shared by the bucketed FPS and the covering pass
+        with _Stage("fps"):
+            landmarks = generate_landmarks(points, min(landmarks, points.shape[0]), fps_h, start_idx=start_idx,
+                                           _cloud=cloud)
     if landmarks.device != points.device:
         raise RuntimeError(f"landmarks.device ({landmarks.device}) != points.device ({points.device})")
     if landmarks.dtype != points.dtype:
@@ -259,11 +317,14 @@ def flood_complex(
     torch.cuda.set_device(device)
 
     lms32 = landmarks.detach().to(torch.float32)
-    cells, gudhi_tree = delaunay_complex(lms32.cpu().numpy())               # host, as in the reference
+    with _Stage("delaunay"):
+        cells, gudhi_tree = delaunay_complex(lms32.cpu().numpy())           # host, as in the reference
     K = cells.shape[1]
     grid_mode = num_rand is None
     max_dimension = min(max_dimension, K - 1)          # degenerate inputs have lower-dimensional cells
-    cloud = PreparedCloud(points)
+    if cloud is None:
+        with _Stage("cloud_build"):
+            cloud = PreparedCloud(points)
     shard = fdist.current_shard()
 
     def launch(d_simplices_np: np.ndarray, weights: torch.Tensor) -> torch.Tensor:
@@ -279,11 +340,14 @@ def flood_complex(
     # and build the face table on the host while the GPU works.
     pending = None
     if grid_mode and max_dimension == K - 1 and cells.shape[0] > 0:
-        pending = launch(cells, _grid_weights(points_per_edge, max_dimension, device))
-    table = FaceTable(cells, n_vertices=lms32.shape[0])
-    values = table.nan_values()           # NaN = not assigned (simplices above max_dimension)
+        with _Stage("kernels"):
+            pending = launch(cells, _grid_weights(points_per_edge, max_dimension, device))
+    with _Stage("face_table"):
+        table = FaceTable(cells, n_vertices=lms32.shape[0])
+        values = table.nan_values()       # NaN = not assigned (simplices above max_dimension)
     if pending is not None:
-        _scatter_face_values(table, pending.cpu().numpy(), values)
+        with _Stage("d2h_scatter"):
+            _scatter_face_values(table, pending.cpu().numpy(), values)
     else:
         for d in range(max_dimension + 1):
             if grid_mode and d < max_dimension:
@@ -313,8 +377,9 @@ def flood_complex(
             return stree
         return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())
 
-    table.make_non_decreasing(values)
-    stree = SimplexTree.from_arrays(table.faces, values)
+    with _Stage("assemble"):
+        table.make_non_decreasing(values)
+        stree = SimplexTree.from_arrays(table.faces, values)
     if return_simplex_tree:
         return stree
     return dict(stree._f)

@@ -127,6 +127,13 @@ int flood_fps_f32(const float *pts, int64_t n, int d, int64_t n_lms, int64_t sta
     return fps(pts, n, d, n_lms, start_idx, out_idx, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int flood_fps_grid_f32(const void *cloud_workspace, const float *pts, int64_t n, int d, int64_t n_lms,
+                       int64_t start_idx, int64_t *out_idx, void *workspace, size_t workspace_bytes,
+                       void *stream) {
+    return fps_grid(cloud_workspace, pts, n, d, n_lms, start_idx, out_idx, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
 size_t flood_cloud_workspace_bytes(int64_t n, int d) {
     if (n < 1 || d < 1 || d > FLOOD_MAX_DIM) return 0;
     return (size_t)cloud_layout(n, d).total;

@@ -59,7 +59,7 @@ __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int p
         ext[a] = from_ordered_bits(bbox[3 + a]) - lo[a];
         if (ext[a] > 0.f) { vol *= (double)ext[a]; ++live; }
     }
-    double target = (double)n / (double)(points_per_cell > 0 ? points_per_cell : 8);
+    double target = (double)n / (double)(points_per_cell > 0 ? points_per_cell : 32);
     if (target < 1.0) target = 1.0;
     if (target > (double)max_cells) target = (double)max_cells;
     float h = 1.0f;
@@ -67,19 +67,20 @@ __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int p
     if (live > 0) {
         h = (float)pow(vol / target, 1.0 / (double)live);
         if (!(h > 0.f)) h = 1.0f;
-        for (int iter = 0; iter < 64; ++iter) {
+        // grow h until every axis fits the 10-bit cell coordinate and the total fits the tables
+        for (int iter = 0; iter < 400; ++iter) {
             int64_t total = 1;
+            bool fits = true;
             for (int a = 0; a < 3; ++a) {
                 int c = 1;
                 if (a < g && ext[a] > 0.f) {
-                    float q = ext[a] / h;
-                    c = q > 2000.f ? 2048 : (int)q + 1;
-                    if (c > 2048) c = 2048;
+                    const float q = ext[a] / h;
+                    if (q >= 1023.f) { fits = false; c = 1024; } else c = (int)q + 1;
                 }
                 nc[a] = c;
                 total *= c;
             }
-            if (total <= max_cells) break;
+            if (fits && total <= max_cells) break;
             h *= 1.15f;
         }
     }
@@ -150,11 +151,12 @@ __global__ void cell_scan_kernel(const GridParams *__restrict__ gpp, int *cell_f
 template <int PD>
 __global__ void scatter_kernel(const float *__restrict__ pts, int64_t n, int d,
                                const int *__restrict__ cell_id, const int *__restrict__ cell_start,
-                               int *cell_fill, float *__restrict__ out) {
+                               int *cell_fill, int *__restrict__ perm, float *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         int c = cell_id[i];
         int64_t pos = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+        perm[pos] = (int)i;
         float rec[PD];
 #pragma unroll
         for (int a = 0; a < PD; ++a) rec[a] = a < d ? pts[i * d + a] : 0.f;
@@ -181,13 +183,14 @@ int cloud_build(const float *pts, int64_t n, int d, int points_per_cell, void *w
     if ((int64_t)ws_bytes < L.total)
         return set_error(FLOOD_E_WORKSPACE, "cloud_build: workspace %zu < %lld bytes", ws_bytes,
                          (long long)L.total);
-    if (points_per_cell <= 0) points_per_cell = get_option("points_per_cell", 8);
+    if (points_per_cell <= 0) points_per_cell = get_option("points_per_cell", 32);
     char *base = static_cast<char *>(ws);
     GridParams *gp = reinterpret_cast<GridParams *>(base + L.off_grid);
     unsigned *bbox = reinterpret_cast<unsigned *>(base + L.off_bbox);
     int *cell_start = reinterpret_cast<int *>(base + L.off_cell_start);
     int *cell_fill = reinterpret_cast<int *>(base + L.off_cell_fill);
     int *cell_id = reinterpret_cast<int *>(base + L.off_cell_id);
+    int *perm = reinterpret_cast<int *>(base + L.off_perm);
     float *out = reinterpret_cast<float *>(base + L.off_points);
 
     const int threads = 256;
@@ -202,9 +205,9 @@ int cloud_build(const float *pts, int64_t n, int d, int points_per_cell, void *w
     cell_count_kernel<<<blocks, threads, 0, st>>>(pts, n, d, gp, cell_id, cell_fill);
     cell_scan_kernel<<<1, 1024, 0, st>>>(gp, cell_fill, cell_start);
     const int pd = record_floats(d);
-    if (pd == 2) scatter_kernel<2><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, out);
-    else if (pd == 4) scatter_kernel<4><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, out);
-    else scatter_kernel<8><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, out);
+    if (pd == 2) scatter_kernel<2><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
+    else if (pd == 4) scatter_kernel<4><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
+    else scatter_kernel<8><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
     FLOOD_LAUNCH_CHECK("cloud_build kernels");
     return FLOOD_OK;
 }

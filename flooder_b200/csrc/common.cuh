@@ -70,6 +70,7 @@ struct CloudLayout {
     int64_t off_cell_start;  // (max_cells + 1) x int32
     int64_t off_cell_fill;   // max_cells x int32 (scratch)
     int64_t off_cell_id;     // n x int32 (scratch)
+    int64_t off_perm;        // n x int32: original index of the i-th cell-sorted point
     int64_t off_points;      // n x record_floats(d) x float, cell-sorted
     int64_t total;
     int64_t max_cells;
@@ -91,6 +92,7 @@ __host__ __device__ inline CloudLayout cloud_layout(int64_t n, int d) {
     L.off_cell_start = o;  o = align_up(o + (L.max_cells + 1) * 4, 256);
     L.off_cell_fill = o;   o = align_up(o + L.max_cells * 4, 256);
     L.off_cell_id = o;     o = align_up(o + n * 4, 256);
+    L.off_perm = o;        o = align_up(o + n * 4, 256);
     L.off_points = o;      o = align_up(o + n * record_floats(d) * 4, 256);
     L.total = o;
     return L;
@@ -103,6 +105,36 @@ __device__ __forceinline__ float cell_coord(float x, float origin, float inv_h) 
 __device__ __forceinline__ int cell_clamp(float g, int n) {
     int i = (int)floorf(g);
     return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+// --------------------------------------------------------------------------------------
+// cell-sorted point records: float2 (d<=2), float4 (d<=4), 2 x float4 (d<=8)
+// --------------------------------------------------------------------------------------
+template <int D> struct Rec;
+template <> struct Rec<2> { using type = float2; };
+template <> struct Rec<3> { using type = float4; };
+template <> struct Rec<4> { using type = float4; };
+template <int D> struct Rec { struct alignas(16) type { float4 a, b; }; };  // D = 5..8
+
+template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]);
+template <> __device__ __forceinline__ void rec_unpack<2>(const float2 &r, float (&p)[2]) { p[0] = r.x; p[1] = r.y; }
+template <> __device__ __forceinline__ void rec_unpack<3>(const float4 &r, float (&p)[3]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; }
+template <> __device__ __forceinline__ void rec_unpack<4>(const float4 &r, float (&p)[4]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; }
+template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]) {
+    const float q[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+    for (int a = 0; a < D; ++a) p[a] = q[a];
+}
+
+template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel();
+template <> __device__ __forceinline__ float2 rec_sentinel<2>() { return make_float2(INFINITY, INFINITY); }
+template <> __device__ __forceinline__ float4 rec_sentinel<3>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
+template <> __device__ __forceinline__ float4 rec_sentinel<4>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
+template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel() {
+    typename Rec<D>::type r;
+    r.a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    r.b = r.a;
+    return r;
 }
 
 // --------------------------------------------------------------------------------------
@@ -122,6 +154,8 @@ int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, 
 int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, float *out,
              cudaStream_t st);
 size_t fps_workspace_bytes(int64_t n, int d, int64_t n_lms);
+int fps_grid(const void *cloud_ws, const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx,
+             int64_t *out_idx, void *ws, size_t ws_bytes, cudaStream_t st);
 int fps(const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx, int64_t *out_idx,
         void *ws, size_t ws_bytes, cudaStream_t st);
 

@@ -164,36 +164,6 @@ __global__ void cover_scan_kernel(long long *v, long long S) {
     if (threadIdx.x == 0) v[S] = carry_s;
 }
 
-// ---------------------------------------------------------------------------------------------
-// point records
-// ---------------------------------------------------------------------------------------------
-template <int D> struct Rec;
-template <> struct Rec<2> { using type = float2; };
-template <> struct Rec<3> { using type = float4; };
-template <> struct Rec<4> { using type = float4; };
-template <int D> struct Rec { struct alignas(16) type { float4 a, b; }; };  // D = 5..8
-
-template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]);
-template <> __device__ __forceinline__ void rec_unpack<2>(const float2 &r, float (&p)[2]) { p[0] = r.x; p[1] = r.y; }
-template <> __device__ __forceinline__ void rec_unpack<3>(const float4 &r, float (&p)[3]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; }
-template <> __device__ __forceinline__ void rec_unpack<4>(const float4 &r, float (&p)[4]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; }
-template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]) {
-    const float q[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
-#pragma unroll
-    for (int a = 0; a < D; ++a) p[a] = q[a];
-}
-
-template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel();
-template <> __device__ __forceinline__ float2 rec_sentinel<2>() { return make_float2(INFINITY, INFINITY); }
-template <> __device__ __forceinline__ float4 rec_sentinel<3>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
-template <> __device__ __forceinline__ float4 rec_sentinel<4>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
-template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel() {
-    typename Rec<D>::type r;
-    r.a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-    r.b = r.a;
-    return r;
-}
-
 // 3-input minimum (FMNMX3 on sm_100a)
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d;

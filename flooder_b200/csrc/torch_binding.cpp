@@ -44,6 +44,22 @@ torch::Tensor fps(const torch::Tensor &pts, int64_t n_lms, int64_t start_idx) {
     return out;
 }
 
+torch::Tensor fps_grid(const torch::Tensor &cloud_ws, const torch::Tensor &pts, int64_t n_lms, int64_t start_idx) {
+    need_cuda_f32(pts, "points");
+    TORCH_CHECK(pts.dim() == 2, "points must be (N, D)");
+    TORCH_CHECK(cloud_ws.is_cuda() && cloud_ws.scalar_type() == torch::kUInt8, "cloud workspace must be CUDA uint8");
+    const c10::cuda::CUDAGuard guard(pts.device());
+    const int64_t n = pts.size(0);
+    const int d = (int)pts.size(1);
+    auto out = torch::empty({n_lms}, pts.options().dtype(torch::kInt64));
+    const size_t wsb = flood_fps_workspace_bytes(n, d, n_lms);
+    auto ws = bytes_like(pts, wsb);
+    check(flood_fps_grid_f32(cloud_ws.data_ptr(), pts.data_ptr<float>(), n, d, n_lms, start_idx,
+                             out.data_ptr<int64_t>(), ws.data_ptr(), wsb, current_stream(pts)),
+          "flood_fps_grid_f32");
+    return out;
+}
+
 torch::Tensor cloud_build(const torch::Tensor &pts, int64_t points_per_cell) {
     need_cuda_f32(pts, "points");
     TORCH_CHECK(pts.dim() == 2, "points must be (N, D)");
@@ -158,6 +174,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "torch loader for the C ABI of libflood_b200.so";
     m.def("abi_version", &flood_abi_version);
     m.def("fps", &fps);
+    m.def("fps_grid", &fps_grid);
     m.def("cloud_build", &cloud_build);
     m.def("bounding_balls", &bounding_balls);
     m.def("covering_radius", &covering_radius);

@@ -61,6 +61,15 @@ size_t flood_fps_workspace_bytes(int64_t n, int d, int64_t n_lms);
 int flood_fps_f32(const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx,
                   int64_t *out_idx, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same result (bit-exact indices) from the bucketed variant: it walks the cell grid of a prepared
+ * cloud (flood_cloud_build_f32 for the same pts / n / d, d >= 2) and only touches the cells whose
+ * running maxima can change -- the pruning idea of the reference's bucket-FPS on the grid the
+ * covering kernel needs anyway.  Workspace size: flood_fps_workspace_bytes().  Reads the grid
+ * header back from the device, i.e. synchronises `stream` once before launching. */
+int flood_fps_grid_f32(const void *cloud_workspace, const float *pts, int64_t n, int d, int64_t n_lms,
+                       int64_t start_idx, int64_t *out_idx, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Cloud preparation: bins the cloud into a uniform cell grid over its first min(d,3) axes and
  * stores it cell-sorted as padded float4 records, so that a ball maps to a few contiguous

@@ -48,6 +48,37 @@ def test_fps_indices(ext, n, d, n_lms, start):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("kind,n,d,n_lms,start,ppc", [
+    ("gauss", 1000, 2, 64, 0, 0), ("gauss", 1000, 3, 1000, 7, 0), ("torus", 50_000, 3, 500, 123, 0),
+    ("gauss", 200_000, 3, 300, 0, 0), ("uniform", 20_000, 5, 128, 5, 0), ("uniform", 5_000, 6, 64, 0, 0),
+    ("uniform", 3_000, 8, 40, 1, 0), ("torus", 30_000, 3, 200, 0, 1), ("torus", 30_000, 3, 200, 0, 500),
+    ("gauss", 400_000, 4, 100, 0, 2), ("gauss", 2, 3, 2, 1, 0),
+])
+def test_fps_grid_indices(ext, kind, n, d, n_lms, start, ppc):
+    """Bucketed FPS on the cell grid == exact FPS, for several cell sizes (ppc = points per cell;
+    1 -> many lanes' worth of cells per warp, 500 -> a handful of big cells)."""
+    pts = _cloud(kind, n, d, seed=n + d)
+    want = native.fps(pts.numpy(), n_lms, start)
+    dev = pts.cuda()
+    ws = ext.cloud_build(dev, ppc)
+    got = ext.fps_grid(ws, dev, n_lms, start).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def test_fps_grid_duplicates_and_barrier(ext):
+    base = _cloud("uniform", 50, 3, seed=9)
+    pts = base.repeat(4, 1)
+    want = native.fps(pts.numpy(), 120, 0)
+    dev = pts.cuda()
+    ws = ext.cloud_build(dev, 4)
+    np.testing.assert_array_equal(ext.fps_grid(ws, dev, 120, 0).cpu().numpy(), want)
+    ext.set_option("fps_barrier", 1)
+    try:
+        np.testing.assert_array_equal(ext.fps_grid(ws, dev, 120, 0).cpu().numpy(), want)
+    finally:
+        ext.set_option("fps_barrier", 0)
+
+
 def test_fps_streaming_mode(ext):
     """Clouds beyond the register-resident capacity use the global-scratch variant."""
     pts = _cloud("gauss", 30_000, 3, seed=3)

@@ -70,6 +70,10 @@ def main():
         kind, n, n_lms, d, ppe = CONFIGS[name]
         pts = cloud(kind, n, d).cuda()
         t_fps, idx = ev_time(lambda: ext.fps(pts, n_lms, 0))
+        t_cloud0, ws0 = ev_time(lambda: ext.cloud_build(pts, 0))
+        t_fpsg, idxg = ev_time(lambda: ext.fps_grid(ws0, pts, n_lms, 0))
+        print(f"   fps brute {t_fps:.2f} ms | fps grid {t_fpsg:.2f} ms (+ cloud {t_cloud0:.2f}) | equal {bool((idx == idxg).all())}")
+        del ws0
         lms = pts[idx]
         t0 = time.perf_counter()
         cells = delaunay_cells(lms.cpu().numpy())
