@@ -16,6 +16,8 @@ from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from .persistence import PersistenceMixin
+
 try:  # pragma: no cover - not available in the build image
     import gudhi as _gudhi
 
@@ -117,7 +119,7 @@ class FaceTable:
             values[k] = np.fmax(values[k], best)
 
 
-class SimplexTree:
+class SimplexTree(PersistenceMixin):
     """Filtered simplicial complex keyed by ascending vertex tuples.
 
     Mirrors the subset of ``gudhi.SimplexTree`` that the reference and its tests touch.

@@ -137,3 +137,51 @@ def test_errors_match_reference():
         fb.flood_complex(X.half(), X[:10].half())
     with pytest.raises(RuntimeError, match="Device not supported"):
         fb.flood_complex(X.cpu(), X[:10].cpu())
+
+
+def _diagrams(tree_or_dict, dims):
+    if isinstance(tree_or_dict, dict):
+        st = fb.SimplexTree()
+        for s, f in tree_or_dict.items():
+            st.insert(s, f)
+    else:
+        st = tree_or_dict
+    st.compute_persistence()
+    return [st.persistence_intervals_in_dimension(d) for d in dims]
+
+
+@pytest.mark.parametrize("use_rand", [True, False])
+@pytest.mark.parametrize("batch_size", [8, 23])
+def test_vs_alpha(use_rand, batch_size):
+    """Reference tests/test_flooder.py:24-75: with L = X the Flood complex has the persistence of
+    the Alpha complex (bottleneck distance < 5e-4 in dimensions 0 and 1).  Alpha filtration and
+    bottleneck distance come from the CPU oracle (gudhi is not installed)."""
+    from oracle import alpha
+
+    seed_all()
+    X = fb.generate_figure_eight_points_2d(1000).to(DEV)
+    kwargs = {"num_rand": 20_000, "points_per_edge": None} if use_rand else {"num_rand": None, "points_per_edge": 130}
+    stree = fb.flood_complex(X, X, return_simplex_tree=True, batch_size=batch_size, **kwargs)
+    flood = _diagrams(stree, range(2))
+    alpha_tree = fb.SimplexTree()
+    for s, f in alpha.alpha_filtration(X.cpu().numpy()).items():
+        alpha_tree.insert(s, f)
+    ref = _diagrams(alpha_tree, range(2))
+    for dim in range(2):
+        dist = alpha.bottleneck_distance(flood[dim], ref[dim])
+        assert dist < 5e-4, f"bottleneck distance {dist} in dimension {dim} (use_rand={use_rand})"
+
+
+def test_persistence_diagrams_match_oracle():
+    """north_star: persistence diagrams (dims 0-2) of the GPU filtration and of the reference CPU
+    filtration agree within 1e-5 relative."""
+    seed_all()
+    X = fb.generate_noisy_torus_points_3d(10_000).to(DEV)
+    L = fb.generate_landmarks(X, 150, start_idx=0)
+    got = _diagrams(fb.flood_complex(X, L, points_per_edge=15), range(3))
+    want = _diagrams(flood_oracle.flood_complex(X.cpu().numpy(), L.cpu().numpy(), points_per_edge=15), range(3))
+    for dim in range(3):
+        assert got[dim].shape == want[dim].shape, f"dimension {dim}: different number of intervals"
+        fin = np.isfinite(want[dim])
+        np.testing.assert_allclose(got[dim][fin], want[dim][fin], rtol=1e-5, atol=1e-7)
+        assert np.array_equal(np.isinf(got[dim]), np.isinf(want[dim]))
