@@ -26,7 +26,7 @@ static std::map<std::string, int> g_options;
 int get_option(const char *name, int fallback) {
     std::lock_guard<std::mutex> lock(g_opt_mutex);
     auto it = g_options.find(name);
-    return it == g_options.end() ? fallback : it->second;
+    return (it == g_options.end() || it->second < 0) ? fallback : it->second;   // negative = unset
 }
 
 struct KernelTimer {
@@ -97,7 +97,7 @@ int flood_device_info(int *sm_count, int *sm_clock_khz) {
 int flood_set_option(const char *name, int value) {
     if (!name) return 0;
     std::lock_guard<std::mutex> lock(g_opt_mutex);
-    int prev = 0;
+    int prev = -1;   // -1: the option was unset (library default in effect)
     auto it = g_options.find(name);
     if (it != g_options.end()) prev = it->second;
     g_options[name] = value;

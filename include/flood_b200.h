@@ -128,7 +128,7 @@ int flood_covering_plan_f32(const void *cloud_workspace, int64_t n, int d, const
 int flood_face_max_f32(const float *min_dist2, int64_t S, int64_t R, const int32_t *support,
                        int K, float *out, void *stream);
 
-/* Tuning knobs for experiments (process-wide; return the previous value).  */
+/* Tuning knobs for experiments (process-wide; returns the previous value, -1 if it was unset). */
 int flood_set_option(const char *name, int value);
 
 /* With option "time_kernels" = 1 the library brackets its dominant kernels with CUDA events on the

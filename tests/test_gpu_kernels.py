@@ -65,18 +65,13 @@ def test_fps_grid_indices(ext, kind, n, d, n_lms, start, ppc):
     np.testing.assert_array_equal(got, want)
 
 
-def test_fps_grid_duplicates_and_barrier(ext):
+def test_fps_grid_duplicates(ext):
     base = _cloud("uniform", 50, 3, seed=9)
     pts = base.repeat(4, 1)
     want = native.fps(pts.numpy(), 120, 0)
     dev = pts.cuda()
     ws = ext.cloud_build(dev, 4)
     np.testing.assert_array_equal(ext.fps_grid(ws, dev, 120, 0).cpu().numpy(), want)
-    ext.set_option("fps_barrier", 1)
-    try:
-        np.testing.assert_array_equal(ext.fps_grid(ws, dev, 120, 0).cpu().numpy(), want)
-    finally:
-        ext.set_option("fps_barrier", 0)
 
 
 def test_fps_streaming_mode(ext):
@@ -91,15 +86,25 @@ def test_fps_streaming_mode(ext):
     np.testing.assert_array_equal(got, want)
 
 
-def test_fps_custom_barrier(ext):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fps_exchange_modes(ext, mode):
+    """Grid-wide argmax via cooperative-groups grid sync (0) or the counter barrier (1, default)."""
     pts = _cloud("gauss", 40_000, 3, seed=4)
     want = native.fps(pts.numpy(), 150, 0)
-    ext.set_option("fps_barrier", 1)
+    dev = pts.cuda()
+    prev = ext.set_option("fps_barrier", mode)
     try:
-        got = ext.fps(pts.cuda(), 150, 0).cpu().numpy()
+        got = ext.fps(dev, 150, 0).cpu().numpy()
+        ws = ext.cloud_build(dev, 0)
+        got_grid = ext.fps_grid(ws, dev, 150, 0).cpu().numpy()
+        ext.set_option("fps_stream", 1)
+        got_stream = ext.fps(dev, 150, 0).cpu().numpy()
     finally:
-        ext.set_option("fps_barrier", 0)
+        ext.set_option("fps_stream", 0)
+        ext.set_option("fps_barrier", prev)
     np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got_grid, want)
+    np.testing.assert_array_equal(got_stream, want)
 
 
 def test_fps_duplicates(ext):
