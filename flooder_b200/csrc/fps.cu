@@ -31,9 +31,9 @@ struct FpsParams {
     unsigned long long *best;  // [n_lms] zero-initialised argmax slots
     float *mind;               // [n] scratch (streaming mode only)
     unsigned *arrive;          // [n_lms] arrival counters (counter barrier only)
-    int custom_barrier;        // 1 (default): one arrival counter per iteration, polled by one thread
-                               // per CTA (3.6 us / iteration at 148 CTAs); 0: cooperative-groups
-                               // grid.sync() (4.1 us)
+    int custom_barrier;        // 0 (default): cooperative-groups grid.sync() (4.1 us / iteration at 148
+                               // CTAs); 1: one arrival counter per iteration polled by one thread per
+                               // CTA (3.6 us, experimental)
 };
 
 template <int D>
@@ -376,7 +376,7 @@ int fps_grid(const void *cloud_ws, const float *pts, int64_t n, int d, int64_t n
     G.out_idx = reinterpret_cast<long long *>(out_idx);
     G.best = reinterpret_cast<unsigned long long *>(base + L.off_best);
     G.arrive = reinterpret_cast<unsigned *>(base + L.off_arrive);
-    G.custom_barrier = get_option("fps_barrier", 1);
+    G.custom_barrier = get_option("fps_barrier", 0);
     FLOOD_CUDA_CHECK(cudaMemsetAsync(base, 0, (size_t)L.off_mind, st));
     // the number of cells lives in device memory: fetch it (one small synchronising copy)
     GridParams host_gp;
@@ -423,7 +423,7 @@ int fps(const float *pts, int64_t n, int d, int64_t n_lms, int64_t start_idx, in
     P.best = reinterpret_cast<unsigned long long *>(base + L.off_best);
     P.arrive = reinterpret_cast<unsigned *>(base + L.off_arrive);
     P.mind = reinterpret_cast<float *>(base + L.off_mind);
-    P.custom_barrier = get_option("fps_barrier", 1);
+    P.custom_barrier = get_option("fps_barrier", 0);
     FLOOD_CUDA_CHECK(cudaMemsetAsync(base, 0, (size_t)L.off_mind, st));
     switch (d) {
         case 1: return dispatch_fps<1>(P, st);
