@@ -25,7 +25,7 @@
 namespace flood {
 namespace {
 
-constexpr int kUnroll = 4;       // candidates per inner-loop trip
+constexpr int kUnroll = 8;       // tiles are padded to a multiple of this (the largest inner-loop unroll)
 
 struct CoverParams {
     const GridParams *gp;
@@ -49,6 +49,7 @@ struct CoverParams {
     int groups_per_block;    // groups handled by one CTA pass (sample block)
     int tile_cap;            // candidate records per shared-memory tile
     int chunk;               // target tested points per chunk
+    int rows_per_chunk_factor;  // chunk >= factor * (cell rows of the simplex)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -124,8 +125,11 @@ __global__ void cover_plan_kernel(CoverParams P, int d) {
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0) {
         P.tested[warp] = (int)total;
-        // number of chunks, stored in place and scanned by cover_scan_kernel
-        if (P.item_base) P.item_base[warp] = (total + P.chunk - 1) / P.chunk;
+        // Number of chunks, stored in place and scanned by cover_scan_kernel.  Every chunk walks the
+        // simplex's row list again, so simplices with many rows get proportionally longer chunks
+        // (the walk stays a few per cent of the chunk's sweep).
+        const long long chunk = max((long long)P.chunk, (long long)P.rows_per_chunk_factor * b.nrows);
+        if (P.item_base) P.item_base[warp] = (total + chunk - 1) / chunk;
     }
 }
 
@@ -225,13 +229,16 @@ constexpr int kMaxWarps = 20;  // warps per CTA
 template <int D, int NT_>
 __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restrict__ tile, int npad,
                                            const float (&x)[kMaxT][D], float (&m)[kMaxT]) {
+    // candidates per trip: warps with few sample groups unroll further to keep enough
+    // independent dependency chains in flight (npad is a multiple of kUnroll = 8)
+    constexpr int U = NT_ <= 2 ? 8 : 4;
 #pragma unroll 1
-    for (int j = 0; j < npad; j += kUnroll) {
-        float p[kUnroll][D];
+    for (int j = 0; j < npad; j += U) {
+        float p[U][D];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
+        for (int u = 0; u < U; ++u) rec_unpack<D>(tile[j + u], p[u]);
 #pragma unroll
-        for (int u = 0; u < kUnroll; u += 2) {
+        for (int u = 0; u < U; u += 2) {
 #pragma unroll
             for (int t = 0; t + 1 < NT_; t += 2) {
                 float2 acc[2];
@@ -258,7 +265,7 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
     }
 }
 
-template <int D>
+template <int D, int PP>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const CoverParams P) {
     using RecT = typename Rec<D>::type;
 
@@ -400,41 +407,59 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (tid == 0) run_pos[NT] = total2;
             __syncthreads();
 
-            for (int base = 0; base < total2; base += NT) {
-                if (fill + NT > tile_cap) {
+            // Each thread takes PP consecutive stream positions per round (PP = 1 for wide CTAs;
+            // narrow CTAs, whose sweeps are short, keep PP record loads in flight per thread):
+            // one binary search for the first position (last run with run_pos <= q), a forward
+            // walk for the others.
+            for (int base = 0; base < total2; base += NT * PP) {
+                if (fill + NT * PP > tile_cap) {
                     accepted += fill;
                     sweep(fill);
                     __syncthreads();
                     fill = 0;
                 }
-                const int q = base + tid;
-                bool pass = false;
-                RecT rec;
-                if (q < total2) {
-                    // last run with run_pos <= q
-                    int lo = 0, hi = NT;
+                const int q0 = base + tid * PP;
+                int lo = 0;
+                if (q0 < total2) {
+                    int hi = NT;
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
-                        if (run_pos[mid] <= q) lo = mid; else hi = mid;
+                        if (run_pos[mid] <= q0) lo = mid; else hi = mid;
                     }
-                    rec = points[run_start[lo] + (q - run_pos[lo])];
-                    float p[D];
-                    rec_unpack<D>(rec, p);
-                    // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
-                    float t = p[0] - c[0];
-                    float acc = t * t;
-#pragma unroll
-                    for (int a2 = 1; a2 < D; ++a2) {
-                        t = p[a2] - c[a2];
-                        acc = fmaf(t, t, acc);
-                    }
-                    pass = acc <= r2;
                 }
-                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                int wbase = 0;
-                if (lane == 0 && ballot) wbase = atomicAdd(&s_fill, __popc(ballot));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (pass) tile[wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
+                RecT rec[PP];
+                bool live[PP];
+#pragma unroll
+                for (int k = 0; k < PP; ++k) {
+                    const int q = q0 + k;
+                    live[k] = q < total2;
+                    if (live[k]) {
+                        while (run_pos[lo + 1] <= q) ++lo;   // skips empty runs; run_pos[NT] = total2 > q
+                        rec[k] = points[run_start[lo] + (q - run_pos[lo])];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < PP; ++k) {
+                    bool pass = false;
+                    if (live[k]) {
+                        float p[D];
+                        rec_unpack<D>(rec[k], p);
+                        // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
+                        float t = p[0] - c[0];
+                        float acc = t * t;
+#pragma unroll
+                        for (int a2 = 1; a2 < D; ++a2) {
+                            t = p[a2] - c[a2];
+                            acc = fmaf(t, t, acc);
+                        }
+                        pass = acc <= r2;
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                    int wbase = 0;
+                    if (lane == 0 && ballot) wbase = atomicAdd(&s_fill, __popc(ballot));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (pass) tile[wbase + __popc(ballot & ((1u << lane) - 1u))] = rec[k];
+                }
                 __syncthreads();
                 fill = s_fill;
             }
@@ -482,7 +507,7 @@ CoverLayout cover_layout(int64_t S) {
 template <int D>
 int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     using RecT = typename Rec<D>::type;
-    auto kern = cover_eval_kernel<D>;
+    constexpr int kNarrowPP = D <= 4 ? 4 : 2;   // stream positions per thread per round, narrow CTAs
     // Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
     // sub-partition), at most kMaxT groups per warp; more than kMaxWarps * kMaxT groups are split
     // into equal sample blocks.
@@ -505,6 +530,8 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     const int forced_cap = get_option("tile_cap", 0);
     if (forced_cap >= NT + kUnroll) cap = forced_cap / kUnroll * kUnroll;
     P.tile_cap = cap;
+    const bool narrow = NT <= 256 && cap >= NT * kNarrowPP + NT && get_option("narrow_pp", 1) != 0;
+    auto kern = narrow ? cover_eval_kernel<D, kNarrowPP> : cover_eval_kernel<D, 1>;
     const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int);
     FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -542,6 +569,7 @@ int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, 
     P.item_base = nullptr;
     P.S = S;
     P.chunk = 1;
+    P.rows_per_chunk_factor = 0;
     const int threads = 128;
     const long long blocks = (S * 32 + threads - 1) / threads;
     cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
@@ -594,6 +622,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
     P.nsb = 1;
     P.chunk = get_option("chunk", 8192);
     if (P.chunk < 256) P.chunk = 256;
+    P.rows_per_chunk_factor = get_option("rows_per_chunk_factor", 32);
 
     FLOOD_CUDA_CHECK(cudaMemsetAsync(P.queue, 0, 64, st));
     if (out_cand_count) FLOOD_CUDA_CHECK(cudaMemsetAsync(out_cand_count, 0, (size_t)S * 8, st));

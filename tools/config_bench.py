@@ -24,6 +24,7 @@ CONFIGS = {
     "uni5d": ("uniform", 2_000_000, 2000, 5, 6),
     "uni6d": ("uniform", 2_000_000, 2000, 6, 4),
     "uni4d": ("uniform", 1_000_000, 1000, 4, 10),
+    "uni5d_small": ("uniform", 500_000, 600, 5, 6),
     "fig8_2d": ("fig8", 1_000_000, 2000, 2, 130),
     "torus_ppe20": ("torus", 1_000_000, 1000, 3, 20),
 }
