@@ -25,7 +25,7 @@
 namespace flood {
 namespace {
 
-constexpr int kUnroll = 8;       // tiles are padded to a multiple of this (the largest inner-loop unroll)
+constexpr int kUnroll = 4;       // candidates per inner-loop trip
 
 struct CoverParams {
     const GridParams *gp;
@@ -229,16 +229,13 @@ constexpr int kMaxWarps = 20;  // warps per CTA
 template <int D, int NT_>
 __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restrict__ tile, int npad,
                                            const float (&x)[kMaxT][D], float (&m)[kMaxT]) {
-    // candidates per trip: warps with few sample groups unroll further to keep enough
-    // independent dependency chains in flight (npad is a multiple of kUnroll = 8)
-    constexpr int U = NT_ <= 2 ? 8 : 4;
 #pragma unroll 1
-    for (int j = 0; j < npad; j += U) {
-        float p[U][D];
+    for (int j = 0; j < npad; j += kUnroll) {
+        float p[kUnroll][D];
 #pragma unroll
-        for (int u = 0; u < U; ++u) rec_unpack<D>(tile[j + u], p[u]);
+        for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
 #pragma unroll
-        for (int u = 0; u < U; u += 2) {
+        for (int u = 0; u < kUnroll; u += 2) {
 #pragma unroll
             for (int t = 0; t + 1 < NT_; t += 2) {
                 float2 acc[2];
@@ -265,7 +262,7 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
     }
 }
 
-template <int D, int PP>
+template <int D>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const CoverParams P) {
     using RecT = typename Rec<D>::type;
 
@@ -407,59 +404,41 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (tid == 0) run_pos[NT] = total2;
             __syncthreads();
 
-            // Each thread takes PP consecutive stream positions per round (PP = 1 for wide CTAs;
-            // narrow CTAs, whose sweeps are short, keep PP record loads in flight per thread):
-            // one binary search for the first position (last run with run_pos <= q), a forward
-            // walk for the others.
-            for (int base = 0; base < total2; base += NT * PP) {
-                if (fill + NT * PP > tile_cap) {
+            for (int base = 0; base < total2; base += NT) {
+                if (fill + NT > tile_cap) {
                     accepted += fill;
                     sweep(fill);
                     __syncthreads();
                     fill = 0;
                 }
-                const int q0 = base + tid * PP;
-                int lo = 0;
-                if (q0 < total2) {
-                    int hi = NT;
+                const int q = base + tid;
+                bool pass = false;
+                RecT rec;
+                if (q < total2) {
+                    // last run with run_pos <= q
+                    int lo = 0, hi = NT;
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
-                        if (run_pos[mid] <= q0) lo = mid; else hi = mid;
+                        if (run_pos[mid] <= q) lo = mid; else hi = mid;
                     }
-                }
-                RecT rec[PP];
-                bool live[PP];
+                    rec = points[run_start[lo] + (q - run_pos[lo])];
+                    float p[D];
+                    rec_unpack<D>(rec, p);
+                    // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
+                    float t = p[0] - c[0];
+                    float acc = t * t;
 #pragma unroll
-                for (int k = 0; k < PP; ++k) {
-                    const int q = q0 + k;
-                    live[k] = q < total2;
-                    if (live[k]) {
-                        while (run_pos[lo + 1] <= q) ++lo;   // skips empty runs; run_pos[NT] = total2 > q
-                        rec[k] = points[run_start[lo] + (q - run_pos[lo])];
+                    for (int a2 = 1; a2 < D; ++a2) {
+                        t = p[a2] - c[a2];
+                        acc = fmaf(t, t, acc);
                     }
+                    pass = acc <= r2;
                 }
-#pragma unroll
-                for (int k = 0; k < PP; ++k) {
-                    bool pass = false;
-                    if (live[k]) {
-                        float p[D];
-                        rec_unpack<D>(rec[k], p);
-                        // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
-                        float t = p[0] - c[0];
-                        float acc = t * t;
-#pragma unroll
-                        for (int a2 = 1; a2 < D; ++a2) {
-                            t = p[a2] - c[a2];
-                            acc = fmaf(t, t, acc);
-                        }
-                        pass = acc <= r2;
-                    }
-                    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                    int wbase = 0;
-                    if (lane == 0 && ballot) wbase = atomicAdd(&s_fill, __popc(ballot));
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    if (pass) tile[wbase + __popc(ballot & ((1u << lane) - 1u))] = rec[k];
-                }
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                int wbase = 0;
+                if (lane == 0 && ballot) wbase = atomicAdd(&s_fill, __popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (pass) tile[wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
                 __syncthreads();
                 fill = s_fill;
             }
@@ -507,7 +486,7 @@ CoverLayout cover_layout(int64_t S) {
 template <int D>
 int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     using RecT = typename Rec<D>::type;
-    constexpr int kNarrowPP = D <= 4 ? 4 : 2;   // stream positions per thread per round, narrow CTAs
+    auto kern = cover_eval_kernel<D>;
     // Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
     // sub-partition), at most kMaxT groups per warp; more than kMaxWarps * kMaxT groups are split
     // into equal sample blocks.
@@ -530,8 +509,6 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     const int forced_cap = get_option("tile_cap", 0);
     if (forced_cap >= NT + kUnroll) cap = forced_cap / kUnroll * kUnroll;
     P.tile_cap = cap;
-    const bool narrow = NT <= 256 && cap >= NT * kNarrowPP + NT && get_option("narrow_pp", 1) != 0;
-    auto kern = narrow ? cover_eval_kernel<D, kNarrowPP> : cover_eval_kernel<D, 1>;
     const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int);
     FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -185,3 +185,38 @@ def test_persistence_diagrams_match_oracle():
         fin = np.isfinite(want[dim])
         np.testing.assert_allclose(got[dim][fin], want[dim][fin], rtol=1e-5, atol=1e-7)
         assert np.array_equal(np.isinf(got[dim]), np.isinf(want[dim]))
+
+
+def test_landmarks_off_the_cloud_and_small_inputs():
+    """Landmarks need not be cloud points (vertex values become > 0); tiny clouds and fewer
+    landmarks than a full-dimensional cell needs still give the oracle's answer."""
+    seed_all(5)
+    X = torch.rand(3000, 3)
+    L = torch.rand(30, 3) * 1.2 - 0.1                      # partly outside the cloud's box
+    got = fb.flood_complex(X.to(DEV), L.to(DEV), points_per_edge=8)
+    want = flood_oracle.flood_complex(X.numpy(), L.numpy(), points_per_edge=8)
+    assert_close_dict(got, want, rtol=RTOL, atol=ATOL)
+    assert min(v for s, v in got.items() if len(s) == 1) > 0
+    # three landmarks in 3-D: one triangle, no tetrahedron
+    got = fb.flood_complex(X.to(DEV), L[:3].to(DEV), points_per_edge=8)
+    want = flood_oracle.flood_complex(X.numpy(), L[:3].numpy(), points_per_edge=8, max_dimension=2)
+    assert set(got) == {(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)}
+    assert_close_dict(got, want, rtol=RTOL, atol=ATOL)
+    # a five-point cloud
+    tiny = X[:5].to(DEV)
+    got = fb.flood_complex(tiny, tiny, points_per_edge=5)
+    want = flood_oracle.flood_complex(X[:5].numpy(), X[:5].numpy(), points_per_edge=5)
+    assert_close_dict(got, want, rtol=RTOL, atol=ATOL)
+
+
+def test_max_dimension_one_in_2d_and_random_mode_dims():
+    seed_all(6)
+    X = fb.generate_figure_eight_points_2d(4000)
+    L = fb.generate_landmarks(X.to(DEV), 50, start_idx=0).cpu()
+    for kwargs in ({"max_dimension": 1, "points_per_edge": 12},
+                   {"max_dimension": 1, "points_per_edge": None, "num_rand": 77}):
+        seed_all(7)
+        got = fb.flood_complex(X.to(DEV), L.to(DEV), **kwargs)
+        seed_all(7)
+        want = flood_oracle.flood_complex(X.numpy(), L.numpy(), **kwargs)
+        assert_close_dict(got, want, rtol=RTOL, atol=ATOL, what=str(kwargs))

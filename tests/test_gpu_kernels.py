@@ -180,7 +180,7 @@ def test_covering_bruteforce(ext, kind, n, d, S, ppe):
 
 
 @pytest.mark.parametrize("option,value", [("chunk", 256), ("warps", 8), ("warps", 3), ("warps", 13),
-                                          ("tile_cap", 700), ("ctas_per_sm", 1), ("warps", 4), ("narrow_pp", 0),
+                                          ("tile_cap", 700), ("ctas_per_sm", 1), ("warps", 4), ("rows_per_chunk_factor", 0),
                                           ("points_per_cell", 1), ("points_per_cell", 64)])
 def test_covering_options(ext, option, value):
     """Chunk splitting (atomicMin merge), other CTA shapes (several sample blocks, uneven
