@@ -48,7 +48,7 @@ WORKLOADS = {
     "torus_10k_100": ("torus", 10_000, 100, 3, 30),
     "gauss_10m_5k": ("gauss", 10_000_000, 5000, 3, 30),
 }
-KERNELS_PER_STEP = 12  # cloud build 6, balls 1, covering 4 (fill, plan, scan, eval), face max 1 (+1 plan when sharded)
+KERNELS_PER_STEP = 13  # cloud build 6, balls 1, covering 5 (fill, plan, scan, eval seed + full), face max 1 (+1 plan when sharded)
 SLOTS_PER_EVAL = {2: 5, 3: 7, 4: 9, 5: 11, 6: 13}
 
 
@@ -339,13 +339,13 @@ def run_cuda(args):
         else:
             parts, mine = None, torch.argsort(r_all, descending=True)
         verts, c, r = verts_all[mine].contiguous(), c_all[mine].contiguous(), r_all[mine].contiguous()
-        md2, cnt, ev = ext.covering_radius(ws, n, dim, verts, weights, None, c, r)
+        md2, cnt, ev, executed = ext.covering_radius(ws, n, dim, verts, weights, None, c, r)
         vals = ext.face_max(md2, support, K)
         if shard is not None:
             vals = fdist.gather_rows(vals, parts, shard)
         else:
             vals = torch.empty_like(vals).index_copy_(0, mine, vals)
-        return vals, ev
+        return vals, ev, executed
 
     def barrier():
         torch.cuda.synchronize()
@@ -373,23 +373,49 @@ def run_cuda(args):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _, ev = device_step()
+        _, ev, executed = device_step()
         b.record()
         b.synchronize()
         step_ms.append(a.elapsed_time(b))
         evals_local = int(ev.item())
+        executed_local = int(executed.item())
     barrier()
     wall_s = time.perf_counter() - wall0
     clock_info = clocks.stop() if rank == 0 else None
     eval_ms_total, eval_launches = ext.kernel_ms("cover_eval", True)
 
+    # the same steps with the exhaustive sweep (every in-ball candidate is evaluated): this is the
+    # kernel the FP32 issue roofline describes; the default path above prunes exactly
+    ext.set_option("prune", 0)
+    for _ in range(2):
+        device_step()
+    barrier()
+    ext.kernel_ms("cover_eval", True)
+    exh_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        device_step()
+        b.record()
+        b.synchronize()
+        exh_ms.append(a.elapsed_time(b))
+    barrier()
+    exh_kernel_total, exh_launches = ext.kernel_ms("cover_eval", True)
+    ext.set_option("prune", -1)
+
     total_ms = torch.tensor([float(np.sum(step_ms))], device=dev, dtype=torch.float64)
     evals_t = torch.tensor([float(evals_local)], device=dev, dtype=torch.float64)
+    executed_t = torch.tensor([float(executed_local)], device=dev, dtype=torch.float64)
     eval_ms_t = torch.tensor([eval_ms_total / max(1, eval_launches)], device=dev, dtype=torch.float64)
+    exh_t = torch.tensor([float(np.sum(exh_ms)), exh_kernel_total / max(1, exh_launches)], device=dev,
+                         dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(executed_t, op=dist.ReduceOp.SUM)
         dist.all_reduce(eval_ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(exh_t, op=dist.ReduceOp.MAX)
     E = evals_t.item()                      # whole job, per step
     ms_per_step = total_ms.item() / args.steps
     value = E / (ms_per_step * 1e-3)
@@ -438,12 +464,28 @@ def run_cuda(args):
                 traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
         except OSError:
             pass
+        executed_frac = executed_t.item() / E
+        exh_kernel_rate = per_launch_evals / (exh_t[1].item() * 1e-3)
+        roofline_exhaustive = {
+            "kernel": "cover_eval_kernel<D, PRUNE=false> (every in-ball candidate evaluated; option prune=0)",
+            "achieved": exh_kernel_rate * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
+            "frac": exh_kernel_rate * slots / peak_slots, "traffic": traffic,
+            "kernel_ms_per_launch": exh_t[1].item(), "kernel_evals_per_s": exh_kernel_rate,
+            "value_evals_per_s": E / (exh_t[0].item() / args.steps * 1e-3),
+            "ms_per_step": exh_t[0].item() / args.steps,
+        }
         roofline = {
             "bound": "fp32-issue (CUDA-core FP32 lane slots; neither HBM nor tensor: contraction length is D=3)",
-            "kernel": "cover_eval_kernel",
+            "kernel": "cover_eval_kernel<D, PRUNE=true>, seed pass + full pass (default product path)",
             "achieved": kernel_rate * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
             "frac": kernel_rate * slots / peak_slots,
-            "traffic": traffic,
+            "note": "achieved counts the ALGORITHMIC evaluations E (reference ball rule). The default sweep skips, "
+                    "exactly, candidates that cannot lower any minimum of a warp (SURVEY 8(f2)), so frac can "
+                    "exceed 1; executed_frac is the share of E actually evaluated, frac_executed the issue-slot "
+                    "utilisation of that executed work, roofline_exhaustive the same step without pruning.",
+            "executed_frac": executed_frac,
+            "frac_executed": kernel_rate * executed_frac * slots / peak_slots,
+            "traffic": None,
             "slots_per_eval": slots, "evals_per_launch": per_launch_evals,
             "kernel_ms_per_launch": eval_ms_t.item(), "kernel_evals_per_s": kernel_rate,
             "peak_evals_per_s": peak_slots / slots,
@@ -478,6 +520,7 @@ def run_cuda(args):
                     "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
             "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps * world,
             "roofline": roofline,
+            "roofline_exhaustive": roofline_exhaustive,
             "roofline_fps": fps_info,
             "clocks": clock_info,
             "timed_region_wall_s": wall_s,

@@ -118,7 +118,7 @@ def load_point_cloud(path: Path) -> Tuple[torch.Tensor, int, int]:
     arr = np.load(path, mmap_mode="r")
     if arr.ndim != 2:
         raise SystemExit(f"expected an (N, D) array, got shape {arr.shape}")
-    pts = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+    pts = torch.from_numpy(np.array(arr, dtype=np.float32, copy=True))
     return pts, int(pts.shape[0]), int(pts.shape[1])
 
 

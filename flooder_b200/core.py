@@ -232,7 +232,7 @@ def covering_values(
     if samples is None and not return_details and verts.shape[0] > 1:
         order = torch.argsort(radii, descending=True)
         verts, centers, radii = verts[order].contiguous(), centers[order].contiguous(), radii[order].contiguous()
-    min_d2, counts, evals = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples, centers, radii)
+    min_d2, counts, evals, _executed = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples, centers, radii)
     support = _support_masks(w) if grid_mode else None
     values = ext.face_max(min_d2, support, K)
     if order is not None:

@@ -42,6 +42,9 @@ struct CoverParams {
     int *tested;             // [S]     plan output
     long long *item_base;    // [S+1]   exclusive prefix of chunks per simplex
     unsigned long long *queue;
+    unsigned long long *executed;   // evaluations actually performed (pruned sweeps skip some)
+    int stream_stride;       // 1 = every stream position; k > 1 = every k-th (seed pass of the pruned mode)
+    int count_work;          // add to cand_count / evals (exactly one pass per call does)
     long long S, R;
     int K;
     int nsb;                 // sample blocks per simplex
@@ -262,7 +265,105 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
     }
 }
 
-template <int D>
+// Pruned sweep (exact).  The warp keeps the axis-aligned box of its sample points and the largest
+// of its running minima u.  A candidate whose distance to that box is at least sqrt(u) cannot lower
+// any of the warp's minima, so it is skipped: lanes test 32 tile records at a time against the
+// box, the survivors (ballot mask) go through the same 4-candidate packed body as sweep_tile.
+// u only shrinks, so a skip stays justified; the minima that come out are bit-identical to the
+// exhaustive sweep (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter
+// candidate rule" of SURVEY.md section 8(f2): the unit of work E is still counted by the
+// reference's ball rule, fewer evaluations are executed.
+template <int D, int NT_>
+__device__ __forceinline__ void sweep_tile_pruned(const typename Rec<D>::type *__restrict__ tile, int n,
+                                                  int sentinel_idx, const float (&x)[kMaxT][D],
+                                                  float (&m)[kMaxT], const float (&blo)[D],
+                                                  const float (&bhi)[D], int lane,
+                                                  unsigned long long &executed) {
+    auto bound = [&]() {
+        float u = m[0];
+#pragma unroll
+        for (int t = 1; t < NT_; ++t) u = fmaxf(u, m[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+        return u;
+    };
+    float u = bound();
+    int pend0 = 0, pend1 = 0, pend2 = 0, npend = 0;
+#pragma unroll 1
+    for (int base = 0;; base += 32) {
+        const bool last = base >= n;   // one extra trip flushes the carried survivors
+        unsigned mask = 0u;
+        if (!last) {
+            const int idx = base + lane;
+            float own[D];
+            rec_unpack<D>(tile[idx < n ? idx : sentinel_idx], own);
+            float box2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                const float e = fmaxf(fmaxf(blo[a] - own[a], own[a] - bhi[a]), 0.f);
+                box2 = fmaf(e, e, box2);
+            }
+            // 0.9999: the box distance and the pair distances are rounded differently
+            mask = __ballot_sync(0xffffffffu, idx < n && box2 * 0.9999f <= u);
+            if (mask == 0u) continue;
+            executed += (unsigned)__popc(mask);
+        }
+        // survivors are swept four at a time; fewer than four are carried over to the next block
+        // (pend0..2, warp-uniform) so that the packed body runs on full groups
+        bool swept = false;
+        while (npend + __popc(mask) >= kUnroll || (last && npend > 0)) {
+            float p[kUnroll][D];
+#pragma unroll
+            for (int v = 0; v < kUnroll; ++v) {
+                int j = sentinel_idx;
+                if (v < npend) {
+                    j = v == 0 ? pend0 : (v == 1 ? pend1 : pend2);
+                } else if (mask) {
+                    j = base + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                }
+                rec_unpack<D>(tile[j], p[v]);
+            }
+            npend = 0;
+            swept = true;
+#pragma unroll
+            for (int v0 = 0; v0 < kUnroll; v0 += 2) {
+#pragma unroll
+                for (int t = 0; t + 1 < NT_; t += 2) {
+                    float2 acc[2];
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        float2 df = __fadd2_rn(make_float2(x[t][0], x[t + 1][0]),
+                                               make_float2(-p[v0 + v][0], -p[v0 + v][0]));
+                        acc[v] = __fmul2_rn(df, df);
+#pragma unroll
+                        for (int a = 1; a < D; ++a) {
+                            df = __fadd2_rn(make_float2(x[t][a], x[t + 1][a]),
+                                            make_float2(-p[v0 + v][a], -p[v0 + v][a]));
+                            acc[v] = __ffma2_rn(df, df, acc[v]);
+                        }
+                    }
+                    m[t] = fmin3(m[t], acc[0].x, acc[1].x);
+                    m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
+                }
+                if (NT_ & 1) {
+                    constexpr int t = NT_ - 1;
+                    m[t] = fmin3(m[t], dist2<D>(x[t], p[v0]), dist2<D>(x[t], p[v0 + 1]));
+                }
+            }
+        }
+        while (mask) {
+            const int jn = base + __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (npend == 0) pend0 = jn; else if (npend == 1) pend1 = jn; else pend2 = jn;
+            ++npend;
+        }
+        if (swept) u = bound();
+        if (last) break;
+    }
+}
+
+template <int D, bool PRUNE>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const CoverParams P) {
     using RecT = typename Rec<D>::type;
 
@@ -284,6 +385,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
     const unsigned long long total_items = (unsigned long long)total_chunks * (unsigned)P.nsb;
 
     if (tid == 0) s_fill = 0;
+    if (tid < kUnroll) tile[tile_cap + tid] = rec_sentinel<D>();   // never overwritten (pruned sweeps pad with them)
+    unsigned long long executed = 0;         // candidates this warp swept in the current item (pruned mode)
+    unsigned long long executed_evals = 0;   // evaluations this warp performed in the whole launch
 
     for (;;) {
         // ---- fetch a work item ---------------------------------------------------------------
@@ -335,8 +439,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
 #pragma unroll
         for (int t = 0; t < kMaxT; ++t) {
             const long long r = (long long)(g0 + t) * 32 + lane;
-            m[t] = INFINITY;
+            // pruned mode starts from what other chunks / the seed pass already found (an upper
+            // bound of the minimum); unused slots carry 0 so that they never loosen the warp bound
+            m[t] = PRUNE ? 0.f : INFINITY;
             if (t < nt && r < P.R) {
+                if (PRUNE) m[t] = __ldcg(P.out + s * P.R + r);
                 if (P.samples) {
 #pragma unroll
                     for (int a = 0; a < D; ++a) x[t][a] = __ldg(P.samples + (s * P.R + r) * D + a);
@@ -360,7 +467,45 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             }
         }
 
-        auto sweep = [&](int n) {
+        // box of this warp's sample points
+        float blo[D], bhi[D];
+        if (PRUNE) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const long long r = (long long)(g0 + t) * 32 + lane;
+                    if (t < nt && r < P.R) { lo = fminf(lo, x[t][a]); hi = fmaxf(hi, x[t][a]); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                }
+                blo[a] = lo;
+                bhi[a] = hi;
+            }
+        }
+
+        auto sweep = [&](int n) __attribute__((always_inline)) {
+            if (PRUNE) {
+                __syncthreads();
+                switch (nt) {  // warp-uniform
+                    case 1: sweep_tile_pruned<D, 1>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 2: sweep_tile_pruned<D, 2>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 3: sweep_tile_pruned<D, 3>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 4: sweep_tile_pruned<D, 4>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 5: sweep_tile_pruned<D, 5>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 6: sweep_tile_pruned<D, 6>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 7: sweep_tile_pruned<D, 7>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 8: sweep_tile_pruned<D, 8>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    default: break;
+                }
+                __syncthreads();
+                if (tid == 0) s_fill = 0;
+                return;
+            }
             const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
             if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
             __syncthreads();
@@ -404,14 +549,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (tid == 0) run_pos[NT] = total2;
             __syncthreads();
 
-            for (int base = 0; base < total2; base += NT) {
+            const int stride = P.stream_stride;
+            for (int base = 0; base * stride < total2; base += NT) {
                 if (fill + NT > tile_cap) {
                     accepted += fill;
                     sweep(fill);
                     __syncthreads();
                     fill = 0;
                 }
-                const int q = base + tid;
+                const int q = (base + tid) * stride;
                 bool pass = false;
                 RecT rec;
                 if (q < total2) {
@@ -455,12 +601,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (t < nt && r < P.R && m[t] < INFINITY)
                 atomicMin(reinterpret_cast<unsigned *>(P.out + s * P.R + r), __float_as_uint(m[t]));
         }
-        if (tid == 0 && sb == 0 && accepted > 0) {
+        if (tid == 0 && sb == 0 && accepted > 0 && P.count_work) {
             if (P.cand_count) atomicAdd(reinterpret_cast<unsigned long long *>(P.cand_count + s),
                                         (unsigned long long)accepted);
             if (P.evals) atomicAdd(P.evals, (unsigned long long)accepted * (unsigned long long)P.R);
         }
+        if (PRUNE) {
+            executed_evals += executed * (unsigned long long)(nt * 32);
+            executed = 0;
+        } else {
+            executed_evals += (unsigned long long)accepted * (unsigned long long)(nt * 32);
+        }
     }
+    if (lane == 0 && executed_evals) atomicAdd(P.executed, executed_evals);
 }
 
 __global__ void fill_inf_kernel(float *p, long long n) {
@@ -486,7 +639,8 @@ CoverLayout cover_layout(int64_t S) {
 template <int D>
 int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     using RecT = typename Rec<D>::type;
-    auto kern = cover_eval_kernel<D>;
+    const bool prune = get_option("prune", 1) != 0;
+    auto kern = prune ? cover_eval_kernel<D, true> : cover_eval_kernel<D, false>;
     // Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
     // sub-partition), at most kMaxT groups per warp; more than kMaxWarps * kMaxT groups are split
     // into equal sample blocks.
@@ -519,7 +673,20 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     const int grid = device_sm_count() * per_sm;
     const bool timed = get_option("time_kernels", 0) != 0;
     if (timed) kernel_timer_start("cover_eval", st);
+    unsigned long long *queue0 = P.queue;
+    const int seed_stride = get_option("seed_stride", 16);
+    if (prune && seed_stride > 1) {
+        // seed pass: every seed_stride-th stream position gives every sample an upper bound of its
+        // minimum, so the full pass prunes from its first tile on
+        P.stream_stride = seed_stride;
+        P.count_work = 0;
+        kern<<<grid, NT, smem, st>>>(P);
+        P.queue = queue0 + 1;
+    }
+    P.stream_stride = 1;
+    P.count_work = 1;
     kern<<<grid, NT, smem, st>>>(P);
+    P.queue = queue0;
     if (timed) kernel_timer_stop("cover_eval", st);
     FLOOD_LAUNCH_CHECK("cover_eval_kernel");
     return FLOOD_OK;
@@ -593,6 +760,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
     P.tested = reinterpret_cast<int *>(wbase + L.off_tested);
     P.item_base = reinterpret_cast<long long *>(wbase + L.off_item_base);
     P.queue = reinterpret_cast<unsigned long long *>(wbase + L.off_queue);
+    P.executed = P.queue + 2;
     P.S = S;
     P.R = R;
     P.K = K;

@@ -88,8 +88,8 @@ std::tuple<torch::Tensor, torch::Tensor> bounding_balls(const torch::Tensor &ver
     return {centers, radii};
 }
 
-// returns (min_dist2 [S,R], cand_count [S] int64, evals [1] int64)
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> covering_radius(
+// returns (min_dist2 [S,R], cand_count [S] int64, evals [1] int64, executed [1] int64)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> covering_radius(
     const torch::Tensor &cloud_ws, int64_t n, int64_t d, const torch::Tensor &verts,
     const torch::Tensor &weights, const c10::optional<torch::Tensor> &samples,
     const torch::Tensor &centers, const torch::Tensor &radii) {
@@ -122,7 +122,11 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> covering_radius(
                                     reinterpret_cast<unsigned long long *>(evals.data_ptr<int64_t>()),
                                     ws.data_ptr(), wsb, current_stream(verts)),
           "flood_covering_radius_f32");
-    return {out, counts, evals};
+    // evaluations actually executed: uint64 at byte FLOOD_COVER_WS_EXECUTED_OFFSET of the workspace
+    auto executed = ws.slice(0, FLOOD_COVER_WS_EXECUTED_OFFSET, FLOOD_COVER_WS_EXECUTED_OFFSET + 8)
+                        .view(torch::kInt64)
+                        .clone();
+    return {out, counts, evals, executed};
 }
 
 torch::Tensor covering_plan(const torch::Tensor &cloud_ws, int64_t n, int64_t d, const torch::Tensor &centers,

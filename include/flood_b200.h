@@ -104,7 +104,15 @@ int flood_bounding_balls_f32(const float *verts, int64_t S, int K, int d, float 
  *   out_cand_count    [S] int64 or NULL: number of cloud points inside ball s
  *   out_evals         host-invisible device counter (1 x uint64) or NULL: sum_s R * cand_count[s],
  *                     the algorithmic work count E of the call
+ *
+ * By default (option "prune" = 1) the sweep is pruned exactly: every warp skips the candidates
+ * that are at least as far from the box of its sample points as its largest running minimum, after
+ * a seed pass over every 16th stream position (option "seed_stride").  The result is bit-identical
+ * to the exhaustive sweep ("prune" = 0); fewer evaluations are executed, E still counts the
+ * reference's ball rule.  The number of evaluations actually executed is left as a uint64 at byte
+ * FLOOD_COVER_WS_EXECUTED_OFFSET of `workspace` (device memory).
  * ------------------------------------------------------------------------------------- */
+#define FLOOD_COVER_WS_EXECUTED_OFFSET 16
 size_t flood_covering_workspace_bytes(int64_t S, int64_t R, int d);
 int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, const float *verts,
                               int64_t S, int K, const float *weights, int64_t R,

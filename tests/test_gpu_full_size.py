@@ -88,7 +88,7 @@ def test_work_count_full_size(torus_1m):
     w = fb.core._grid_weights(30, 3, DEV)
     ws = ext.cloud_build(dev, 0)
     c, r = ext.bounding_balls(verts)
-    md2, cnt, ev = ext.covering_radius(ws, dev.shape[0], 3, verts, w, None, c, r)
+    md2, cnt, ev, executed = ext.covering_radius(ws, dev.shape[0], 3, verts, w, None, c, r)
     assert int(ev.item()) == int(cnt.sum().item()) * w.shape[0]
     rng = np.random.default_rng(1)
     sel = rng.choice(len(cells), size=40, replace=False)

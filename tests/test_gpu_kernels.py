@@ -143,7 +143,7 @@ def _covering_case(ext, pts, verts, weights, samples=None, ppc=0):
     ws = ext.cloud_build(P, ppc)
     c, r = ext.bounding_balls(V)
     smp = None if samples is None else samples.to(dev).contiguous()
-    md2, cnt, ev = ext.covering_radius(ws, P.shape[0], P.shape[1], V, W, smp, c, r)
+    md2, cnt, ev, executed = ext.covering_radius(ws, P.shape[0], P.shape[1], V, W, smp, c, r)
     torch.cuda.synchronize()
     return md2.cpu().numpy(), cnt.cpu().numpy(), int(ev.item()), c.cpu().numpy(), r.cpu().numpy()
 
@@ -200,6 +200,43 @@ def test_covering_options(ext, option, value):
     finally:
         ext.set_option(option, prev)
     _check_against_bruteforce(pts, verts, w, md2, cnt, ev, c, r)
+
+
+@pytest.mark.parametrize("kind,n,d,ppe", [("torus", 60_000, 3, 30), ("gauss", 50_000, 3, 12), ("uniform", 20_000, 2, 40),
+                                         ("uniform", 20_000, 5, 4)])
+def test_pruning_is_exact(ext, kind, n, d, ppe):
+    """Pruned sweep (with and without the seed pass) == exhaustive sweep, bit for bit, and the
+    work counters are unchanged; the pruned modes execute fewer evaluations."""
+    pts = _cloud(kind, n, d, seed=n)
+    g = torch.Generator().manual_seed(3)
+    lms = pts[torch.randperm(n, generator=g)[:60]]
+    from oracle.simplex_tree import delaunay_top_simplices
+
+    cells = delaunay_top_simplices(lms.numpy())[:120]
+    verts = lms[torch.as_tensor(cells)].cuda().contiguous()
+    w = torch.as_tensor(flood_oracle.generate_grid(ppe, d)[0]).cuda()
+    P = pts.cuda()
+    ws = ext.cloud_build(P, 0)
+    c, r = ext.bounding_balls(verts)
+    results = {}
+    for name, opts in {"exhaustive": {"prune": 0}, "pruned": {"prune": 1, "seed_stride": 16},
+                       "pruned_noseed": {"prune": 1, "seed_stride": 1}}.items():
+        prev = {k: ext.set_option(k, v) for k, v in opts.items()}
+        try:
+            md2, cnt, ev, executed = ext.covering_radius(ws, n, d, verts, w, None, c, r)
+            torch.cuda.synchronize()
+            results[name] = (md2.cpu().numpy(), cnt.cpu().numpy(), int(ev.item()), int(executed.item()))
+        finally:
+            for k, v in prev.items():
+                ext.set_option(k, v)
+    ref = results["exhaustive"]
+    assert ref[3] >= ref[2]                                   # exhaustive executes every evaluation (+ padding)
+    for name in ("pruned", "pruned_noseed"):
+        got = results[name]
+        np.testing.assert_array_equal(got[0], ref[0])
+        np.testing.assert_array_equal(got[1], ref[1])
+        assert got[2] == ref[2]
+        assert got[3] < ref[3]
 
 
 def test_covering_explicit_samples_and_random_weights(ext):

@@ -85,12 +85,14 @@ def main():
         c, r = ext.bounding_balls(verts)
         order = torch.argsort(r, descending=True)
         verts, c, r = verts[order].contiguous(), c[order].contiguous(), r[order].contiguous()
-        t_cov, (md2, cnt, evals) = ev_time(lambda: ext.covering_radius(ws, n, d, verts, w, None, c, r), reps=2)
+        t_cov, (md2, cnt, evals, executed) = ev_time(lambda: ext.covering_radius(ws, n, d, verts, w, None, c, r), reps=2)
         E = int(evals.item())
         peak = sms * 128 * 1.965e9 / SLOTS[d]
         print(f"[{name}] n={n} lms={n_lms} d={d} ppe={ppe} S={len(cells)} R={w.shape[0]} opts={opts}")
         print(f"   fps {t_fps:.2f} ms ({n * (4 * d + 8) * (n_lms - 1) / t_fps / 1e6:.0f} GB/s algorithmic) | "
               f"delaunay {t_del * 1e3:.0f} ms | cloud_build {t_cloud:.2f} ms | covering {t_cov:.2f} ms")
+        ex = int(executed.item())
+        print(f"   executed/E = {ex / max(E, 1):.3f}")
         print(f"   E={E:.4e} evals/s={E / (t_cov * 1e-3):.4e} frac_of_issue_roofline={E / (t_cov * 1e-3) / peak:.3f} "
               f"cand/simplex mean {cnt.float().mean().item():.0f} max {cnt.max().item()}", flush=True)
         if n_lms <= 2000 and d <= 3:

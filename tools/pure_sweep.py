@@ -26,7 +26,7 @@ for rep in range(4):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    md2, cnt, ev = ext.covering_radius(ws, n, 3, verts, w, None, c, r)
+    md2, cnt, ev, executed = ext.covering_radius(ws, n, 3, verts, w, None, c, r)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b); E = int(ev.item())
     print(f"opts={opts} {ms:.2f} ms E={E:.3e} evals/s={E/ms*1e3:.4e} frac={E/ms*1e3/5.3178e12:.3f} cand/simplex={cnt.float().mean().item():.0f}")

@@ -45,7 +45,7 @@ def main():
     w, _, _ = fb.generate_grid(30, 3, "cuda")
     t_cloud, ws = ev_time(lambda: ext.cloud_build(pts, 0))
     c, r = ext.bounding_balls(verts)
-    t_cov, (md2, cnt, evals) = ev_time(lambda: ext.covering_radius(ws, n, 3, verts, w, None, c, r))
+    t_cov, (md2, cnt, evals, executed) = ev_time(lambda: ext.covering_radius(ws, n, 3, verts, w, None, c, r))
     E = int(evals.item())
     print(f"n={n} lms={n_lms} S={len(cells)} R={w.shape[0]} opts={opts}")
     print(f"fps {t_fps:.2f} ms | delaunay {t_del*1e3:.1f} ms | cloud_build {t_cloud:.2f} ms | covering {t_cov:.2f} ms")
