@@ -219,8 +219,6 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &
 // ---------------------------------------------------------------------------------------------
 // the persistent evaluation kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxT = 8;       // sample groups (32 samples each) per warp
-constexpr int kMaxWarps = 20;  // warps per CTA
 
 // Sweep of a padded tile by one warp that holds NT_ sample groups in registers: the hot loop.
 // Two samples share one packed FP32x2 instruction (FADD2 / FMUL2 / FFMA2 take the candidate
@@ -229,9 +227,9 @@ constexpr int kMaxWarps = 20;  // warps per CTA
 // for four evaluations.  An odd group is handled with the scalar form.  Each lane result is the
 // same IEEE operation as the scalar form (x - p, round; *, round; fma, round), so the minima are
 // bit-identical to a scalar evaluation.
-template <int D, int NT_>
+template <int D, int NT_, int MAXT>
 __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restrict__ tile, int npad,
-                                           const float (&x)[kMaxT][D], float (&m)[kMaxT]) {
+                                           const float (&x)[MAXT][D], float (&m)[MAXT]) {
 #pragma unroll 1
     for (int j = 0; j < npad; j += kUnroll) {
         float p[kUnroll][D];
@@ -273,10 +271,10 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
 // exhaustive sweep (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter
 // candidate rule" of SURVEY.md section 8(f2): the unit of work E is still counted by the
 // reference's ball rule, fewer evaluations are executed.
-template <int D, int NT_>
+template <int D, int NT_, int MAXT>
 __device__ __forceinline__ void sweep_tile_pruned(const typename Rec<D>::type *__restrict__ tile, int n,
-                                                  int sentinel_idx, const float (&x)[kMaxT][D],
-                                                  float (&m)[kMaxT], const float (&blo)[D],
+                                                  int sentinel_idx, const float (&x)[MAXT][D],
+                                                  float (&m)[MAXT], const float (&blo)[D],
                                                   const float (&bhi)[D], int lane,
                                                   unsigned long long &executed) {
     auto bound = [&]() {
@@ -363,8 +361,12 @@ __device__ __forceinline__ void sweep_tile_pruned(const typename Rec<D>::type *_
     }
 }
 
-template <int D, bool PRUNE>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const CoverParams P) {
+// MAXT = sample groups per warp held in registers, MAXW = warps per CTA, MINB = CTAs per SM the
+// register budget is sized for: (8, 20, 1) is the wide shape; (4, 16, 2) trades registers for
+// twice the warps per SM, which the latency-bound pruned sweep needs.
+template <int D, bool PRUNE, int MAXT, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
+    constexpr int kMaxT = MAXT;
     using RecT = typename Rec<D>::type;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -492,14 +494,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (PRUNE) {
                 __syncthreads();
                 switch (nt) {  // warp-uniform
-                    case 1: sweep_tile_pruned<D, 1>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 2: sweep_tile_pruned<D, 2>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 3: sweep_tile_pruned<D, 3>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 4: sweep_tile_pruned<D, 4>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 5: sweep_tile_pruned<D, 5>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 6: sweep_tile_pruned<D, 6>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 7: sweep_tile_pruned<D, 7>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 8: sweep_tile_pruned<D, 8>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 1: if constexpr (1 <= MAXT) sweep_tile_pruned<D, 1, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 2: if constexpr (2 <= MAXT) sweep_tile_pruned<D, 2, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 3: if constexpr (3 <= MAXT) sweep_tile_pruned<D, 3, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 4: if constexpr (4 <= MAXT) sweep_tile_pruned<D, 4, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 5: if constexpr (5 <= MAXT) sweep_tile_pruned<D, 5, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 6: if constexpr (6 <= MAXT) sweep_tile_pruned<D, 6, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 7: if constexpr (7 <= MAXT) sweep_tile_pruned<D, 7, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
+                    case 8: if constexpr (8 <= MAXT) sweep_tile_pruned<D, 8, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
                     default: break;
                 }
                 __syncthreads();
@@ -510,14 +512,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) cover_eval_kernel(const Cov
             if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
             __syncthreads();
             switch (nt) {  // warp-uniform
-                case 1: sweep_tile<D, 1>(tile, npad, x, m); break;
-                case 2: sweep_tile<D, 2>(tile, npad, x, m); break;
-                case 3: sweep_tile<D, 3>(tile, npad, x, m); break;
-                case 4: sweep_tile<D, 4>(tile, npad, x, m); break;
-                case 5: sweep_tile<D, 5>(tile, npad, x, m); break;
-                case 6: sweep_tile<D, 6>(tile, npad, x, m); break;
-                case 7: sweep_tile<D, 7>(tile, npad, x, m); break;
-                case 8: sweep_tile<D, 8>(tile, npad, x, m); break;
+                case 1: if constexpr (1 <= MAXT) sweep_tile<D, 1, MAXT>(tile, npad, x, m); break;
+                case 2: if constexpr (2 <= MAXT) sweep_tile<D, 2, MAXT>(tile, npad, x, m); break;
+                case 3: if constexpr (3 <= MAXT) sweep_tile<D, 3, MAXT>(tile, npad, x, m); break;
+                case 4: if constexpr (4 <= MAXT) sweep_tile<D, 4, MAXT>(tile, npad, x, m); break;
+                case 5: if constexpr (5 <= MAXT) sweep_tile<D, 5, MAXT>(tile, npad, x, m); break;
+                case 6: if constexpr (6 <= MAXT) sweep_tile<D, 6, MAXT>(tile, npad, x, m); break;
+                case 7: if constexpr (7 <= MAXT) sweep_tile<D, 7, MAXT>(tile, npad, x, m); break;
+                case 8: if constexpr (8 <= MAXT) sweep_tile<D, 8, MAXT>(tile, npad, x, m); break;
                 default: break;
             }
             __syncthreads();
@@ -636,25 +638,25 @@ CoverLayout cover_layout(int64_t S) {
     return L;
 }
 
-template <int D>
-int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
+// launch with a given kernel shape: MAXT groups per warp, at most MAXW warps per CTA
+template <int D, bool PRUNE, int MAXT, int MAXW, int MINB>
+int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
     using RecT = typename Rec<D>::type;
-    const bool prune = get_option("prune", 1) != 0;
-    auto kern = prune ? cover_eval_kernel<D, true> : cover_eval_kernel<D, false>;
+    auto kern = cover_eval_kernel<D, PRUNE, MAXT, MAXW, MINB>;
     // Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
-    // sub-partition), at most kMaxT groups per warp; more than kMaxWarps * kMaxT groups are split
-    // into equal sample blocks.
+    // sub-partition), at most MAXT groups per warp; more than MAXW * MAXT groups are split into
+    // equal sample blocks.
     const int G = (int)((R + 31) / 32);
     auto warps_for = [](int groups) {
         if (groups < 4) return groups < 1 ? 1 : groups;
-        int w = (groups + kMaxT - 1) / kMaxT;
+        int w = (groups + MAXT - 1) / MAXT;
         w = (w + 3) / 4 * 4;
-        return w > kMaxWarps ? kMaxWarps : w;
+        return w > MAXW ? MAXW : w;
     };
     int forced = get_option("warps", 0);
-    if (forced < 0 || forced > kMaxWarps) forced = 0;
+    if (forced < 0 || forced > MAXW) forced = 0;
     int W = forced ? forced : warps_for(G);
-    P.nsb = (G + W * kMaxT - 1) / (W * kMaxT);
+    P.nsb = (G + W * MAXT - 1) / (W * MAXT);
     P.groups = G;
     P.groups_per_block = (G + P.nsb - 1) / P.nsb;
     if (!forced) W = warps_for(P.groups_per_block);
@@ -675,7 +677,7 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     if (timed) kernel_timer_start("cover_eval", st);
     unsigned long long *queue0 = P.queue;
     const int seed_stride = get_option("seed_stride", 16);
-    if (prune && seed_stride > 1) {
+    if (PRUNE && seed_stride > 1) {
         // seed pass: every seed_stride-th stream position gives every sample an upper bound of its
         // minimum, so the full pass prunes from its first tile on
         P.stream_stride = seed_stride;
@@ -690,6 +692,16 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     if (timed) kernel_timer_stop("cover_eval", st);
     FLOOD_LAUNCH_CHECK("cover_eval_kernel");
     return FLOOD_OK;
+}
+
+template <int D>
+int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
+    const bool prune = get_option("prune", 1) != 0;
+    // One shape for both modes: 8 sample groups per warp, up to 20 warps, one CTA per SM for wide
+    // sample sets.  (A thin shape -- 4 groups per warp, 16 warps, 2 CTAs per SM -- prunes more,
+    // 26 % instead of 37 % of E executed on the torus, but its per-record overhead makes it slower.)
+    if (!prune) return launch_eval_shape<D, false, 8, 20, 1>(P, R, st);
+    return launch_eval_shape<D, true, 8, 20, 1>(P, R, st);
 }
 
 }  // namespace
