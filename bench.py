@@ -458,10 +458,12 @@ def run_cuda(args):
         # dominant kernel: evaluations of the slowest rank's launch / its event time
         per_launch_evals = E / world
         kernel_rate = per_launch_evals / (eval_ms_t.item() * 1e-3)
-        traffic = None
+        traffic = traffic_pruned = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-                traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
+                entry = json.load(fh).get(args.workload, {})
+                traffic = entry.get("dram_bytes_per_launch")
+                traffic_pruned = entry.get("pruned_dram_bytes_per_step")
         except OSError:
             pass
         executed_frac = executed_t.item() / E
@@ -485,7 +487,7 @@ def run_cuda(args):
                     "utilisation of that executed work, roofline_exhaustive the same step without pruning.",
             "executed_frac": executed_frac,
             "frac_executed": kernel_rate * executed_frac * slots / peak_slots,
-            "traffic": None,
+            "traffic": traffic_pruned,
             "slots_per_eval": slots, "evals_per_launch": per_launch_evals,
             "kernel_ms_per_launch": eval_ms_t.item(), "kernel_evals_per_s": kernel_rate,
             "peak_evals_per_s": peak_slots / slots,
