@@ -13,9 +13,13 @@
 //     lengths and gathers its window of the stream with a binary search per point;
 //   * every gathered point is tested against the ball (the reference predicate) and the
 //     survivors are compacted with warp ballots into a shared-memory tile of float4 records;
-//   * when the tile fills up, all warps sweep it: each thread keeps T sample points and their
+//   * when the tile fills up, all warps sweep it: each thread keeps up to 8 sample points and their
 //     running minima in registers, tile records are broadcast LDS.128 reads, the distance is the
-//     direct difference form in FP32 FMA (D sub, 1 mul, D-1 fma, 1 min per pair);
+//     direct difference form in FP32 (D sub, 1 mul, D-1 fma, 1 min per pair), issued as packed
+//     FP32x2 instructions and 3-input minima (sweep_tile);
+//   * by default the sweep is pruned exactly: a warp skips the tile records that are at least as
+//     far from the box of its samples as its largest running minimum (sweep_tile_pruned), after
+//     a seed pass over a sub-sampled stream has given every sample a finite bound;
 //   * the minima are merged into min_dist2 with an unsigned atomicMin (non-negative floats order
 //     like their bit patterns), because a simplex may be split over several chunks.
 //
@@ -537,10 +541,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             if (row < bc.nrows) row_run(bc, row, gp, P.cell_start, a, len);
             int batch_total;
             const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
-            const int batch_lo = carry;
             carry += batch_total;
             if (carry <= win_lo) continue;
-            (void)batch_lo;
             // clip the run to this chunk's window of the stream
             const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
             const int len2 = max(0, s1 - s0);
