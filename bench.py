@@ -521,6 +521,10 @@ def run_cuda(args):
                     "stage_seconds_serialised": stage_seconds,
                     "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
             "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps * world,
+            "value_note": "E / step time of the default product path, whose sweep is pruned EXACTLY (bit-identical "
+                          "minima; executed_frac of E is evaluated, SURVEY 8(f2)); value_exhaustive is the same step "
+                          "with every evaluation executed (option prune=0), the kernel roofline_exhaustive describes",
+            "value_exhaustive": roofline_exhaustive["value_evals_per_s"],
             "roofline": roofline,
             "roofline_exhaustive": roofline_exhaustive,
             "roofline_fps": fps_info,
