@@ -43,6 +43,10 @@ def ext():
         loader.exec_module(mod)
         if mod.abi_version() != 1:
             raise ImportError(f"libflood_b200 ABI {mod.abi_version()} != 1")
+        # FLOODER_B200_OPTIONS="name=value,..." presets library options (experiments / diagnostics)
+        for item in filter(None, os.environ.get("FLOODER_B200_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            mod.set_option(name.strip(), int(value))
         _ext = mod
     return _ext
 
@@ -68,11 +72,13 @@ def cdll() -> ctypes.CDLL:
         lib.flood_covering_workspace_bytes.restype = c_sz
         lib.flood_covering_radius_f32.argtypes = [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64,
                                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+        lib.flood_covering_bricks.argtypes = [c_i64, c_int, c_vp, c_int, ctypes.POINTER(c_int)]
         lib.flood_covering_plan_f32.argtypes = [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]
         lib.flood_face_max_f32.argtypes = [c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]
         lib.flood_set_option.argtypes = [ctypes.c_char_p, c_int]
         for fn in ("flood_device_info", "flood_fps_f32", "flood_fps_grid_f32", "flood_cloud_build_f32", "flood_bounding_balls_f32",
-                   "flood_covering_radius_f32", "flood_covering_plan_f32", "flood_face_max_f32", "flood_set_option"):
+                   "flood_covering_radius_f32", "flood_covering_plan_f32", "flood_covering_bricks", "flood_face_max_f32",
+                   "flood_set_option"):
             getattr(lib, fn).restype = c_int
         _lib = lib
     return _lib
@@ -84,5 +90,6 @@ EXPORTED_SYMBOLS = [
     "flood_cloud_workspace_bytes", "flood_cloud_build_f32",
     "flood_bounding_balls_f32",
     "flood_covering_workspace_bytes", "flood_covering_radius_f32", "flood_covering_plan_f32",
+    "flood_covering_bricks",
     "flood_face_max_f32",
 ]

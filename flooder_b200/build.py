@@ -24,11 +24,13 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(OUT, "libflood_b200.so")
 EXT = os.path.join(OUT, "_flood_ext.so")
 
-CU_SOURCES = ["abi.cu", "cloud.cu", "balls.cu", "covering.cu", "fps.cu"]
+CU_SOURCES = ["abi.cu", "cloud.cu", "balls.cu", "covering.cu", "fps.cu"] + [f"covering_d{d}.cu" for d in range(1, 9)]
+CU_HEADERS = ["common.cuh", "covering_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--threads", "4", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ = os.path.join(OUT, "obj")
 
 
 def _nvcc() -> str:
@@ -46,15 +48,35 @@ def _stale(target: str, sources) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "flood_b200.h")]
-    if force or _stale(LIB, deps):
-        os.makedirs(OUT, exist_ok=True)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB, *srcs]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
+    """One object per .cu (compiled in parallel: the evaluation kernel is instantiated per ambient
+    dimension in its own translation unit), then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    headers = [os.path.join(CSRC, h) for h in CU_HEADERS] + [os.path.join(INCLUDE, "flood_b200.h")]
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    for name in CU_SOURCES:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(OBJ, name[:-3] + ".o")
+        if force or _stale(obj, [src] + headers):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append(cmd)
+    if jobs:
+        def run(cmd):
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            return cmd, res
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            for cmd, res in pool.map(run, jobs):
+                if verbose or res.returncode != 0:
+                    print(" ".join(cmd))
+                    print(res.stdout + res.stderr)
+                if res.returncode != 0:
+                    raise subprocess.CalledProcessError(res.returncode, cmd)
+    objs = [os.path.join(OBJ, name[:-3] + ".o") for name in CU_SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs], check=True)
     return LIB
 
 

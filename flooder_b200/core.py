@@ -21,6 +21,7 @@ import torch
 
 from . import _native
 from . import distributed as fdist
+from .bricks import brick_order
 from .simplex_tree import FaceTable, SimplexTree, delaunay_complex
 
 _SUPPORTED_DTYPES = (torch.float32, torch.float64)
@@ -107,6 +108,7 @@ def _grid_weights_cached(n: int, dim: int, device_str: str) -> torch.Tensor:
     counts = torch.as_tensor(_lattice(n, dim), device=device_str)
     weights = torch.empty(counts.shape, dtype=torch.float32, device=device_str)
     torch.divide(counts, n - 1, out=weights)
+    weights._flood_cached = True
     return weights
 
 
@@ -120,6 +122,35 @@ def _support_masks(weights: torch.Tensor) -> torch.Tensor:
     K = weights.shape[1]
     bits = (weights != 0).to(torch.int32) << torch.arange(K, device=weights.device, dtype=torch.int32)
     return bits.sum(dim=1).to(torch.int32).contiguous()
+
+
+# Sample order handed to the kernel: every warp's brick of samples spatially compact (bricks.py).
+# FLOODER_B200_BRICKS=0 keeps the reference's order (diagnostics).
+USE_BRICKS = os.environ.get("FLOODER_B200_BRICKS", "1") != "0"
+_brick_cache: Dict[tuple, tuple] = {}
+
+
+def _kernel_sample_order(weights: torch.Tensor, dim: int, cache_key=None):
+    """``(perm, weights[perm])`` for the brick layout the kernel reports for these options, or
+    ``(None, weights)``.  ``cache_key`` identifies read-only weights (the cached lattice)."""
+    R, K = weights.shape
+    if not USE_BRICKS or K < 2 or R <= 32:
+        return None, weights
+    groups, per_block = _native.ext().covering_bricks(int(R), int(dim))
+    key = None
+    if cache_key is not None:
+        key = (cache_key, str(weights.device), tuple(groups), per_block)
+        hit = _brick_cache.get(key)
+        if hit is not None:
+            return hit
+    perm_np = brick_order(weights.detach().cpu().numpy(), groups, per_block)
+    perm = torch.as_tensor(perm_np, device=weights.device)
+    out = (perm, weights[perm].contiguous())
+    if key is not None:
+        if len(_brick_cache) > 64:
+            _brick_cache.clear()
+        _brick_cache[key] = out
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -208,6 +239,18 @@ class PreparedCloud:
         self.workspace = _native.ext().cloud_build(pts32, int(points_per_cell))
 
 
+def _slab_rows(S: int, R: int, device) -> int:
+    """Simplices per kernel call such that the (rows, R) float32 ``min_dist2`` buffer stays within
+    a quarter of the free device memory (at most 8 GiB).  The reference bounds the same buffer with
+    ``batch_size`` (``flooder/core.py:193-226``); here one call normally takes every simplex."""
+    free, _total = torch.cuda.mem_get_info(device)
+    budget = min(free // 4, 8 << 30)
+    override = os.environ.get("FLOODER_B200_SLAB_BYTES")
+    if override:
+        budget = int(override)
+    return max(1, min(S, int(budget // (4 * max(R, 1)))))
+
+
 def covering_values(
     cloud: PreparedCloud,
     simplex_vertices: torch.Tensor,
@@ -224,21 +267,43 @@ def covering_values(
     ext = _native.ext()
     verts = simplex_vertices.to(torch.float32).contiguous()
     w = weights.to(torch.float32).contiguous()
-    K = verts.shape[1]
+    S, K = verts.shape[0], verts.shape[1]
+    perm = None
+    if samples is None:
+        # the lattice weights are cached per device and never modified: key the order by identity
+        cache_key = ("lattice", tuple(w.shape), w.data_ptr()) if getattr(weights, "_flood_cached", False) else None
+        perm, w = _kernel_sample_order(w, cloud.d, cache_key)
+    support = _support_masks(w) if grid_mode else None
     centers, radii = ext.bounding_balls(verts)
     # Largest balls first: the kernel's work queue follows the simplex order, so the big items
     # are dealt out early and the small ones fill the tail of the launch.
     order = None
-    if samples is None and not return_details and verts.shape[0] > 1:
+    if samples is None and not return_details and S > 1:
         order = torch.argsort(radii, descending=True)
         verts, centers, radii = verts[order].contiguous(), centers[order].contiguous(), radii[order].contiguous()
-    min_d2, counts, evals, _executed = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples, centers, radii)
-    support = _support_masks(w) if grid_mode else None
-    values = ext.face_max(min_d2, support, K)
+    rows = S if return_details else _slab_rows(S, w.shape[0], verts.device)
+    if rows >= S:
+        min_d2, counts, evals, executed = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples,
+                                                              centers, radii)
+        values = ext.face_max(min_d2, support, K)
+    else:
+        # memory-bounded: the simplices go through the kernel in slabs, only the face values stay
+        parts = []
+        for lo in range(0, S, rows):
+            hi = min(S, lo + rows)
+            min_d2, _c, _e, _x = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts[lo:hi], w,
+                                                     None if samples is None else samples[lo:hi].contiguous(),
+                                                     centers[lo:hi], radii[lo:hi])
+            parts.append(ext.face_max(min_d2, support, K))
+            del min_d2
+        values = torch.cat(parts, dim=0)
     if order is not None:
         values = torch.empty_like(values).index_copy_(0, order, values)
     if return_details:
-        return values, dict(min_dist2=min_d2, cand_count=counts, evals=evals, centers=centers, radii=radii)
+        if perm is not None:            # per-sample output back in the caller's sample order
+            min_d2 = torch.empty_like(min_d2).index_copy_(1, perm, min_d2)
+        return values, dict(min_dist2=min_d2, cand_count=counts, evals=evals, executed=executed,
+                            centers=centers, radii=radii)
     return values
 
 
@@ -290,13 +355,20 @@ def flood_complex(
     del batch_size, use_triton
     if max_dimension is None:
         max_dimension = points.shape[1]
+    if points.dim() != 2 or points.shape[1] < 1 or points.shape[1] > 8:
+        raise RuntimeError(f"points must have shape (N, D) with 1 <= D <= 8, got {tuple(points.shape)}")
     if PROFILE_STAGES:
         last_stage_seconds.clear()
     cloud = None
+    landmarks_arg = landmarks
     if isinstance(landmarks, Integral):
         if points.device.type == "cuda" and points.dtype in _SUPPORTED_DTYPES:
             with _Stage("cloud_build"):
                 cloud = PreparedCloud(points)      # shared by the bucketed FPS and the covering pass
+        if start_idx is None and fdist.current_shard() is not None:
+            # a random start index is drawn by rank 0 and shared: every rank must select the
+            # same landmarks (FPS itself is deterministic)
+            start_idx = fdist.broadcast_int(fdist.current_shard(), int(np.random.randint(len(points))), points.device)
         with _Stage("fps"):
             landmarks = generate_landmarks(points, min(landmarks, points.shape[0]), fps_h, start_idx=start_idx,
                                            _cloud=cloud)
@@ -316,16 +388,23 @@ def flood_complex(
     _require_cuda(points, "points")
     torch.cuda.set_device(device)
 
+    shard = fdist.current_shard()
+    del landmarks_arg
     lms32 = landmarks.detach().to(torch.float32)
     with _Stage("delaunay"):
-        cells, gudhi_tree = delaunay_complex(lms32.cpu().numpy())           # host, as in the reference
+        # host, as in the reference; triangulated in the precision the landmarks were given in
+        cells, gudhi_tree = delaunay_complex(landmarks.detach().cpu().numpy())
     K = cells.shape[1]
     grid_mode = num_rand is None
     max_dimension = min(max_dimension, K - 1)          # degenerate inputs have lower-dimensional cells
     if cloud is None:
         with _Stage("cloud_build"):
             cloud = PreparedCloud(points)
-    shard = fdist.current_shard()
+    if shard is not None:
+        # every rank must hold the same complex, or the all-gather below mixes rows up
+        digest_input = np.concatenate([np.asarray(cells.shape, dtype=np.int64), cells.reshape(-1),
+                                       lms32.cpu().numpy().view(np.int32).reshape(-1).astype(np.int64)])
+        fdist.assert_same_on_all_ranks(shard, digest_input, device, "landmarks / Delaunay cells")
 
     def launch(d_simplices_np: np.ndarray, weights: torch.Tensor) -> torch.Tensor:
         """Enqueue one dimension pass (asynchronous); returns the device tensor of values."""
@@ -364,22 +443,39 @@ def flood_complex(
                 _scatter_face_values(sub, host_values, values)
             else:
                 weights = generate_uniform_weights(num_rand, d, device, torch.float32)
+                if shard is not None:
+                    # the weights come from each process's own CPU generator (core.py:423-425 of the
+                    # reference): rank 0's draw is used everywhere so that a value does not depend
+                    # on which rank evaluated it
+                    fdist.broadcast_tensor(shard, weights)
                 values[d + 1] = launch(d_cells, weights).cpu().numpy()[:, 0].astype(np.float64)
 
-    if gudhi_tree is not None:  # pragma: no cover  (gudhi is not in the build image)
+    with _Stage("assemble"):
+        # grid mode on full-dimensional cells is monotone by construction (face samples are a subset
+        # of coface samples, and the minimum over cofaces preserves that); everything else goes
+        # through make_filtration_non_decreasing like the reference (core.py:280)
+        monotone = pending is not None
+        return _write_back(table, values, gudhi_tree, return_simplex_tree, monotone)
+
+
+def _write_back(table: FaceTable, values: Dict[int, np.ndarray], gudhi_tree, return_simplex_tree: bool,
+                monotone: bool = False):
+    """Reference ``core.py:278-288``: assign the values, make the filtration non-decreasing, return
+    the tree or ``{tuple(simplex): value}``.  With gudhi the container is gudhi's own tree (the
+    reference's contract); otherwise the array-backed stand-in."""
+    if gudhi_tree is not None:
         stree = gudhi_tree
         for k, faces in table.faces.items():
             for simplex, value in zip(faces.tolist(), values[k].tolist()):
-                if value == value:
+                if value == value:          # NaN = not assigned (above max_dimension)
                     stree.assign_filtration(simplex, value)
         stree.make_filtration_non_decreasing()
         if return_simplex_tree:
             return stree
         return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())
-
-    with _Stage("assemble"):
+    if not monotone:
         table.make_non_decreasing(values)
-        stree = SimplexTree.from_arrays(table.faces, values)
+    stree = SimplexTree.from_arrays(table.faces, values)
     if return_simplex_tree:
         return stree
-    return dict(stree._f)
+    return stree.to_flat_dict()

@@ -161,6 +161,10 @@ int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, con
                            (cudaStream_t)stream);
 }
 
+int flood_covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block) {
+    return covering_bricks(R, d, out_groups, capacity, bricks_per_block);
+}
+
 int flood_covering_plan_f32(const void *cloud_workspace, int64_t n, int d, const float *centers,
                             const float *radii, int64_t S, int32_t *out_tested, void *stream) {
     return covering_plan(cloud_workspace, n, d, centers, radii, S, out_tested, (cudaStream_t)stream);

@@ -6,10 +6,13 @@ namespace flood {
 namespace {
 
 // Reference rule, flooder/core.py:156-172.  One thread per simplex (S is at most a few
-// million; the kernel is bandwidth-trivial).  Arithmetic is float32 with explicit rounding:
-// the centre is the midpoint of the first longest edge in row-major (i0, i1) order, the
-// radius is scaled and padded with two separately rounded operations like the torch
-// expression `amax * factor + 1e-3`.
+// million; the kernel is bandwidth-trivial).  Arithmetic is float32 with explicit rounding and
+// NO fused multiply-add: squared differences are rounded, then added in coordinate order, then
+// the square root is taken -- the same operation sequence as the oracle
+// (oracle/flood_oracle.py::bounding_balls), so that near-ties between edges resolve identically.
+// The centre is the midpoint of the first maximum of the flattened K x K distance matrix in
+// row-major (i0, i1) order (core.py:157-161); the radius is scaled and padded with two
+// separately rounded operations like the torch expression `amax * factor + 1e-3`.
 __global__ void bounding_balls_kernel(const float *__restrict__ verts, int64_t S, int K, int d,
                                       float *__restrict__ centers, float *__restrict__ radii) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -21,10 +24,10 @@ __global__ void bounding_balls_kernel(const float *__restrict__ verts, int64_t S
         for (int j = 0; j < K; ++j) {
             float acc = 0.f;
             for (int a = 0; a < d; ++a) {
-                float t = v[i * d + a] - v[j * d + a];
-                acc = fmaf(t, t, acc);
+                const float t = __fsub_rn(v[i * d + a], v[j * d + a]);
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
             }
-            float dist = sqrtf(acc);
+            const float dist = __fsqrt_rn(acc);
             if (dist > best) { best = dist; b0 = i; b1 = j; }
         }
     float c[FLOOD_MAX_DIM];
@@ -36,10 +39,10 @@ __global__ void bounding_balls_kernel(const float *__restrict__ verts, int64_t S
     for (int k = 0; k < K; ++k) {
         float acc = 0.f;
         for (int a = 0; a < d; ++a) {
-            float t = v[k * d + a] - c[a];
-            acc = fmaf(t, t, acc);
+            const float t = __fsub_rn(v[k * d + a], c[a]);
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
         }
-        far = fmaxf(far, sqrtf(acc));
+        far = fmaxf(far, __fsqrt_rn(acc));
     }
     const float factor = (K - 1) > 1 ? 1.42f : 1.01f;
     radii[s] = __fadd_rn(__fmul_rn(far, factor), 1e-3f);

@@ -111,12 +111,14 @@ __device__ __forceinline__ int cell_clamp(float g, int n) {
 // cell-sorted point records: float2 (d<=2), float4 (d<=4), 2 x float4 (d<=8)
 // --------------------------------------------------------------------------------------
 template <int D> struct Rec;
+template <> struct Rec<1> { using type = float2; };
 template <> struct Rec<2> { using type = float2; };
 template <> struct Rec<3> { using type = float4; };
 template <> struct Rec<4> { using type = float4; };
 template <int D> struct Rec { struct alignas(16) type { float4 a, b; }; };  // D = 5..8
 
 template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D>::type &r, float (&p)[D]);
+template <> __device__ __forceinline__ void rec_unpack<1>(const float2 &r, float (&p)[1]) { p[0] = r.x; }
 template <> __device__ __forceinline__ void rec_unpack<2>(const float2 &r, float (&p)[2]) { p[0] = r.x; p[1] = r.y; }
 template <> __device__ __forceinline__ void rec_unpack<3>(const float4 &r, float (&p)[3]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; }
 template <> __device__ __forceinline__ void rec_unpack<4>(const float4 &r, float (&p)[4]) { p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; }
@@ -127,6 +129,7 @@ template <int D> __device__ __forceinline__ void rec_unpack(const typename Rec<D
 }
 
 template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel();
+template <> __device__ __forceinline__ float2 rec_sentinel<1>() { return make_float2(INFINITY, INFINITY); }
 template <> __device__ __forceinline__ float2 rec_sentinel<2>() { return make_float2(INFINITY, INFINITY); }
 template <> __device__ __forceinline__ float4 rec_sentinel<3>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
 template <> __device__ __forceinline__ float4 rec_sentinel<4>() { return make_float4(INFINITY, INFINITY, INFINITY, INFINITY); }
@@ -135,6 +138,18 @@ template <int D> __device__ __forceinline__ typename Rec<D>::type rec_sentinel()
     r.a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     r.b = r.a;
     return r;
+}
+
+// read-only (non-coherent) load of one record
+template <int D> __device__ __forceinline__ typename Rec<D>::type rec_ldg(const typename Rec<D>::type *p) {
+    if constexpr (D <= 4) {
+        return __ldg(p);
+    } else {
+        typename Rec<D>::type r;
+        r.a = __ldg(&p->a);
+        r.b = __ldg(&p->b);
+        return r;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -149,6 +164,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
                     const float *weights, int64_t R, const float *samples, const float *centers,
                     const float *radii, float *out_min_dist2, int64_t *out_cand_count,
                     unsigned long long *out_evals, void *ws, size_t ws_bytes, cudaStream_t st);
+int covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block);
 int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, const float *radii,
                   int64_t S, int32_t *out_tested, cudaStream_t st);
 int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, float *out,

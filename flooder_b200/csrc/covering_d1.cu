@@ -1,0 +1,6 @@
+// cover_eval_kernel for ambient dimension D = 1 (see covering_kernels.cuh)
+#include "covering_kernels.cuh"
+
+namespace flood {
+template int dispatch_eval<1>(CoverParams &, int64_t, cudaStream_t);
+}  // namespace flood

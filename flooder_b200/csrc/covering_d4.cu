@@ -1,0 +1,6 @@
+// cover_eval_kernel for ambient dimension D = 4 (see covering_kernels.cuh)
+#include "covering_kernels.cuh"
+
+namespace flood {
+template int dispatch_eval<4>(CoverParams &, int64_t, cudaStream_t);
+}  // namespace flood

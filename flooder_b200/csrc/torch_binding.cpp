@@ -129,6 +129,17 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> covering_
     return {out, counts, evals, executed};
 }
 
+// (groups per brick, bricks per CTA) -- host-side layout query
+std::tuple<std::vector<int64_t>, int64_t> covering_bricks(int64_t R, int64_t d) {
+    int per_block = 0;
+    const int n = flood_covering_bricks(R, (int)d, nullptr, 0, &per_block);
+    check(n < 0 ? n : FLOOD_OK, "flood_covering_bricks");
+    std::vector<int32_t> g((size_t)n);
+    check(flood_covering_bricks(R, (int)d, g.data(), n, &per_block) < 0 ? FLOOD_E_INVALID : FLOOD_OK,
+          "flood_covering_bricks");
+    return {std::vector<int64_t>(g.begin(), g.end()), (int64_t)per_block};
+}
+
 torch::Tensor covering_plan(const torch::Tensor &cloud_ws, int64_t n, int64_t d, const torch::Tensor &centers,
                             const torch::Tensor &radii) {
     need_cuda_f32(centers, "centers");
@@ -184,6 +195,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("covering_radius", &covering_radius);
     m.def("face_max", &face_max);
     m.def("covering_plan", &covering_plan);
+    m.def("covering_bricks", &covering_bricks);
     m.def("set_option", &set_option);
     m.def("kernel_ms", &kernel_ms);
 }

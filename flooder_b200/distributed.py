@@ -98,3 +98,45 @@ def sharded_covering_values(
     mine = parts[shard.rank]
     local = compute(simplex_vertices[mine].contiguous())
     return gather_rows(local, parts, shard)
+
+
+def broadcast_int(shard: Shard, value: int, device) -> int:
+    """Rank 0's ``value`` on every rank (used for the random FPS start index)."""
+    import torch.distributed as dist
+
+    dev = device if dist.get_backend(shard.group) == "nccl" else "cpu"
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0, group=shard.group)
+    return int(t.item())
+
+
+def broadcast_tensor(shard: Shard, tensor: torch.Tensor) -> torch.Tensor:
+    """In place: rank 0's contents on every rank."""
+    import torch.distributed as dist
+
+    if dist.get_backend(shard.group) != "nccl" and tensor.device.type != "cpu":
+        host = tensor.cpu()
+        dist.broadcast(host, src=0, group=shard.group)
+        tensor.copy_(host)
+    else:
+        dist.broadcast(tensor, src=0, group=shard.group)
+    return tensor
+
+
+def assert_same_on_all_ranks(shard: Shard, array, device, what: str) -> None:
+    """Raise on every rank if ``array`` (numpy, integer) differs between ranks: the sharded pass
+    all-gathers rows by position, so all ranks must hold the same simplex list."""
+    import numpy as np
+    import torch.distributed as dist
+
+    a = np.ascontiguousarray(array, dtype=np.int64).reshape(-1)
+    # position-weighted checksum + length; int64 wrap-around is fine for an equality check
+    with np.errstate(over="ignore"):
+        digest = int((a * (np.arange(a.size, dtype=np.int64) * 2654435761 + 1)).sum()) & 0x3FFFFFFFFFFFFFFF
+    dev = device if dist.get_backend(shard.group) == "nccl" else "cpu"
+    t = torch.tensor([digest, -digest, a.size, -a.size], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=shard.group)
+    lo_hi = t.tolist()
+    if lo_hi[0] != -lo_hi[1] or lo_hi[2] != -lo_hi[3]:
+        raise RuntimeError(f"flooder_b200: {what} differ between ranks; the sharded pass needs identical inputs "
+                           "on every rank (same points, same landmarks or the same integer landmark count)")

@@ -18,24 +18,49 @@ import numpy as np
 
 from .persistence import PersistenceMixin
 
-try:  # pragma: no cover - not available in the build image
+try:
     import gudhi as _gudhi
 
     HAS_GUDHI = hasattr(_gudhi, "DelaunayComplex")
-except Exception:  # noqa: BLE001
+except Exception:  # noqa: BLE001  (gudhi is not in the build image; tests inject a stand-in)
     _gudhi = None
     HAS_GUDHI = False
 
 
 def delaunay_cells(landmarks: np.ndarray) -> np.ndarray:
-    """Top-dimensional Delaunay cells as ascending vertex index rows, shape (S, D+1)."""
+    """Top-dimensional Delaunay cells as ascending vertex index rows, shape (S, D+1).
+
+    Qhull stand-in for ``gudhi.DelaunayComplex`` (``flooder/core.py:130-132``).  The landmarks
+    are triangulated in the precision they are given in (the reference hands its landmark tensor
+    to gudhi as is).  1-D landmarks need no Qhull: the cells are the consecutive pairs of the
+    sorted coordinates.  Degenerate inputs are reported instead of silently changing the complex:
+    affinely dependent landmarks raise, landmarks Qhull leaves out (duplicates) warn."""
+    import warnings
+
     from scipy.spatial import Delaunay
+    from scipy.spatial import QhullError
 
     pts = np.asarray(landmarks, dtype=np.float64)
     n, d = pts.shape
     if n <= d:  # not enough points for a full-dimensional cell
         return np.arange(n, dtype=np.int64)[None, :]
-    cells = Delaunay(pts).simplices.astype(np.int64)
+    if d == 1:
+        order = np.argsort(pts[:, 0], kind="stable")
+        cells = np.stack([order[:-1], order[1:]], axis=1).astype(np.int64)
+        cells.sort(axis=1)
+        return cells
+    try:
+        tri = Delaunay(pts)
+    except QhullError as exc:
+        raise RuntimeError(
+            f"the {n} landmarks do not span {d} dimensions (Qhull: {str(exc).splitlines()[0]}); the Qhull "
+            "stand-in cannot triangulate degenerate landmark sets -- install gudhi, which flooder_b200 "
+            "uses for the Delaunay step when it is importable") from exc
+    if tri.coplanar.size:
+        warnings.warn(
+            f"{tri.coplanar.shape[0]} of {n} landmarks are not vertices of the Delaunay triangulation "
+            "(duplicate or degenerate points); they do not appear in the complex", RuntimeWarning, stacklevel=3)
+    cells = tri.simplices.astype(np.int64)
     cells.sort(axis=1)
     return cells
 
@@ -233,11 +258,16 @@ class SimplexTree(PersistenceMixin):
     def to_dict(self) -> Dict[Tuple[int, ...], float]:
         return {tuple(s): v for s, v in self.get_simplices()}
 
+    def to_flat_dict(self) -> Dict[Tuple[int, ...], float]:
+        """``{simplex: value}`` as ``flood_complex`` returns it (insertion order: by dimension, then
+        lexicographic -- the order of ``get_simplices`` for a tree built by ``from_arrays``)."""
+        return dict(self._f)
+
 
 def delaunay_complex(landmarks: np.ndarray):
     """Host Delaunay step.  Returns ``(cells, gudhi_tree_or_None)``: with gudhi installed the
     triangulation and the container are gudhi's (as in the reference), otherwise Qhull's cells."""
-    if HAS_GUDHI:  # pragma: no cover
+    if HAS_GUDHI:
         tree = _gudhi.DelaunayComplex(np.asarray(landmarks)).create_simplex_tree()
         width = landmarks.shape[1] + 1
         cells = np.asarray([s for s, _ in tree.get_simplices() if len(s) == width], dtype=np.int64)

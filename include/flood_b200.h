@@ -121,6 +121,16 @@ int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, con
                               unsigned long long *out_evals, void *workspace,
                               size_t workspace_bytes, void *stream);
 
+/* Sample layout of the evaluation kernel (host-side query, no device work).  The kernel keeps the
+ * samples of a simplex in registers, "brick" by brick: brick i = out_groups[i] consecutive groups of
+ * 32 samples held by one warp; *bricks_per_block consecutive bricks belong to one CTA.  A caller
+ * that is free to order its samples (the weights of flood_complex are shared by all simplices,
+ * flooder/core.py:182-188) should make every brick spatially compact: the exact pruning then skips
+ * more candidates.  The result does not depend on the order.  Returns the number of bricks
+ * (out_groups may be NULL to query it) or a negative error code.  Depends on the options in
+ * effect ("prune", "shape", "warps"). */
+int flood_covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block);
+
 /* Cost estimate: out_tested[s] = number of cloud points in the cell rows touched by ball s (an
  * upper bound of cand_count[s], obtained from the cell table alone).  New with the multi-GPU
  * sharding (the reference is single-GPU): the host balances simplices over ranks with it. */

@@ -90,14 +90,22 @@ def bounding_balls(simplex_vertices: np.ndarray, d: int) -> Tuple[np.ndarray, np
     v = np.asarray(simplex_vertices)
     dt = v.dtype.type
     S, K, D = v.shape
-    diff = v[:, :, None, :] - v[:, None, :, :]
-    pair = np.sqrt((diff * diff).sum(axis=3, dtype=v.dtype))  # (S,K,K)
-    flat = pair.reshape(S, K * K).argmax(axis=1)
+
+    def norms(diff):
+        # squares rounded in the input dtype and added in coordinate order (no pairwise
+        # re-association, no fused multiply-add): the operation sequence is part of the
+        # contract, near-ties between edges must resolve the same way everywhere
+        acc = np.zeros(diff.shape[:-1], dtype=v.dtype)
+        for a in range(diff.shape[-1]):
+            acc = acc + diff[..., a] * diff[..., a]
+        return np.sqrt(acc)
+
+    pair = norms(v[:, :, None, :] - v[:, None, :, :])          # (S,K,K)
+    flat = pair.reshape(S, K * K).argmax(axis=1)               # first maximum, row-major
     i0, i1 = np.divmod(flat, K)
     ar = np.arange(S)
     centers = (v[ar, i0] + v[ar, i1]) / dt(2.0)
-    off = v - centers[:, None, :]
-    far = np.sqrt((off * off).sum(axis=2, dtype=v.dtype)).max(axis=1)
+    far = norms(v - centers[:, None, :]).max(axis=1)
     radii = far * dt(1.42 if d > 1 else 1.01) + dt(1e-3)
     return centers.astype(v.dtype), radii.astype(v.dtype)
 

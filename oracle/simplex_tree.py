@@ -30,6 +30,10 @@ def delaunay_top_simplices(points: np.ndarray) -> np.ndarray:
     if pts.shape[0] <= pts.shape[1]:
         # fewer points than needed for a full-dimensional cell: a single simplex
         return np.arange(pts.shape[0], dtype=np.int64)[None, :]
+    if pts.shape[1] == 1:
+        # 1-D: the Delaunay triangulation is the chain of consecutive points (Qhull needs >= 2-D)
+        order = np.argsort(pts[:, 0], kind="stable")
+        return np.sort(np.stack([order[:-1], order[1:]], axis=1).astype(np.int64), axis=1)
     tri = Delaunay(pts)
     return np.sort(tri.simplices.astype(np.int64), axis=1)
 

@@ -195,3 +195,111 @@ def test_landmark_argument_errors():
         fb.generate_landmarks(torch.rand(10, 2), 0)
     with pytest.raises(RuntimeError, match="must be positive"):
         fb.generate_landmarks(torch.rand(10, 2), -3)
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: 1-D / degenerate landmark sets, the gudhi branch, brick ordering
+# ------------------------------------------------------------------------------------------
+def test_delaunay_cells_1d_and_degenerate():
+    x = np.array([[0.3], [0.1], [0.9], [0.5]])
+    cells = delaunay_cells(x)
+    assert sorted(map(tuple, cells.tolist())) == [(0, 1), (0, 3), (2, 3)]
+    np.testing.assert_array_equal(np.sort(cells, axis=0), np.sort(delaunay_top_simplices(x), axis=0))
+    # affinely dependent landmarks: a clear error instead of a raw QhullError
+    flat = np.random.default_rng(0).random((20, 3))
+    flat[:, 2] = 0.0
+    with pytest.raises(RuntimeError, match="do not span"):
+        delaunay_cells(flat)
+    # duplicated landmarks are left out by Qhull: reported, not silent
+    pts = np.random.default_rng(1).random((30, 2))
+    dup = np.concatenate([pts, pts[:3]])
+    with pytest.warns(RuntimeWarning, match="not vertices"):
+        cells = delaunay_cells(dup)
+    assert cells.max() < 33
+
+
+def _fake_gudhi():
+    import types
+
+    from oracle import simplex_tree as ost
+
+    g = types.ModuleType("gudhi")
+    g.DelaunayComplex = ost.DelaunayComplex
+    g.SimplexTree = ost.DictSimplexTree
+    return g
+
+
+def test_gudhi_branch_with_injected_module(monkeypatch):
+    """The reference's container contract (flooder/core.py:130-132, 278-288): with gudhi importable
+    the Delaunay step and the returned tree are gudhi's.  gudhi is not in the image, so the
+    oracle's stand-in module is injected in its place."""
+    from flooder_b200 import simplex_tree as st
+
+    monkeypatch.setattr(st, "_gudhi", _fake_gudhi())
+    monkeypatch.setattr(st, "HAS_GUDHI", True)
+    rng = np.random.default_rng(3)
+    lms = rng.random((40, 3))
+    cells, tree = st.delaunay_complex(lms)
+    assert tree is not None and isinstance(tree, DictSimplexTree)
+    np.testing.assert_array_equal(np.unique(cells, axis=0), np.unique(delaunay_cells(lms), axis=0))
+    table = FaceTable(cells, n_vertices=40)
+    values = {k: rng.random(len(f)) for k, f in table.faces.items()}
+    values[4][:] = np.nan                                     # "above max_dimension": stays unassigned
+    want_vals = {k: v.copy() for k, v in values.items()}
+    got_tree = core._write_back(table, {k: v.copy() for k, v in values.items()}, tree, True)
+    assert got_tree is tree                                   # gudhi's own tree is returned
+    got = core._write_back(table, {k: v.copy() for k, v in values.items()},
+                           st.delaunay_complex(lms)[1], False)
+    # same as the stand-in path
+    table.make_non_decreasing(want_vals)
+    want = SimplexTree.from_arrays(table.faces, want_vals).to_flat_dict()
+    assert set(got) == set(want)
+    for key, v in want.items():
+        assert (np.isnan(v) and np.isnan(got[key])) or got[key] == v, key
+    for simplex, f in tree.get_simplices():                   # filtered complex
+        for _face, ff in tree.get_boundaries(simplex):
+            assert not (ff > f)
+
+
+def test_brick_order_is_a_compact_permutation():
+    from flooder_b200.bricks import brick_order
+
+    w, _, _ = flood_oracle.generate_grid(30, 3)
+    groups = [8, 8, 8, 7] * 5                                 # flood_covering_bricks for R = 4960, narrow shape
+    perm = brick_order(w, groups, 4)
+    assert sorted(perm.tolist()) == list(range(len(w)))
+
+    # axis-aligned boxes of the bricks on a (rotated) regular tetrahedron with unit edges
+    verts = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], float) / np.sqrt(8)
+    q, _ = np.linalg.qr(np.random.default_rng(0).normal(size=(3, 3)))
+    x = w.astype(np.float64) @ verts @ q.T
+
+    def mean_box_volume(order):
+        vol, pos = [], 0
+        for g in groups:
+            idx = order[pos:pos + g * 32]
+            pos += g * 32
+            vol.append(np.prod(x[idx].max(axis=0) - x[idx].min(axis=0) + 0.1))
+        return np.mean(vol)
+
+    assert mean_box_volume(perm) < 0.25 * mean_box_volume(np.arange(len(w)))
+    # ragged tail, tiny sets, random weights
+    for R, gs, per in [(252, [2, 2, 2, 2], 4), (33, [1, 1], 2), (5000, [8] * 19 + [5], 4)]:
+        ww = np.random.default_rng(R).dirichlet(np.ones(4), size=R).astype(np.float32)
+        p = brick_order(ww, gs, per)
+        assert sorted(p.tolist()) == list(range(R))
+    with pytest.raises(ValueError):
+        brick_order(w, [8] * 3, 4)
+
+
+def test_covering_bricks_query_without_gpu():
+    """Host-side layout query of the C ABI (no device work)."""
+    ext = _native.ext()
+    groups, per_block = ext.covering_bricks(4960, 3)
+    assert sum(groups) == 155 and len(groups) % per_block == 0 and max(groups) <= 8
+    groups, per_block = ext.covering_bricks(252, 5)
+    assert sum(groups) == 8
+    groups, per_block = ext.covering_bricks(1, 3)
+    assert sum(groups) == 1
+    lib = _native.cdll()
+    assert lib.flood_covering_bricks(0, 3, None, 0, None) == -1

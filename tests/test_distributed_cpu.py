@@ -71,3 +71,42 @@ def test_sharded_values_gloo_world2(tmp_path, n_rows):
 
 def test_no_process_group_means_no_shard():
     assert fdist.current_shard() is None
+
+
+def _consistency_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shard = fdist.current_shard()
+        # rank 0's draw wins (random FPS start index, random weights)
+        assert fdist.broadcast_int(shard, 100 + rank, "cpu") == 100
+        w = torch.full((5, 3), float(rank))
+        fdist.broadcast_tensor(shard, w)
+        assert torch.equal(w, torch.zeros(5, 3))
+        same = np.arange(30).reshape(10, 3)
+        fdist.assert_same_on_all_ranks(shard, same, "cpu", "cells")          # identical: passes
+        different = same + (rank == 1)
+        try:
+            fdist.assert_same_on_all_ranks(shard, different, "cpu", "cells")
+            raised = False
+        except RuntimeError as exc:
+            raised = "differ between ranks" in str(exc)
+        shorter = same[: 10 - rank]
+        try:
+            fdist.assert_same_on_all_ranks(shard, shorter, "cpu", "cells")
+            raised_len = False
+        except RuntimeError:
+            raised_len = True
+        np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([raised, raised_len]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_consistency_helpers_gloo_world2(tmp_path):
+    """Every rank must derive the same landmarks / cells / weights: rank 0's random
+    draws are broadcast, and differing simplex lists raise on EVERY rank instead of hanging or
+    mis-scattering rows in the all-gather."""
+    mp.spawn(_consistency_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        assert np.load(tmp_path / f"ok{rank}.npy").all()

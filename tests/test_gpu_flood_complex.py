@@ -220,3 +220,77 @@ def test_max_dimension_one_in_2d_and_random_mode_dims():
         seed_all(7)
         want = flood_oracle.flood_complex(X.numpy(), L.numpy(), **kwargs)
         assert_close_dict(got, want, rtol=RTOL, atol=ATOL, what=str(kwargs))
+
+
+# ------------------------------------------------------------------------------------------
+# round 2
+# ------------------------------------------------------------------------------------------
+def test_one_dimensional_cloud():
+    """The reference is dimension-generic (flooder/core.py:146-188); 1-D clouds go through the same
+    kernels (records padded with a zero coordinate) and give the oracle's values."""
+    seed_all(8)
+    X = torch.rand(5000, 1)
+    L = fb.generate_landmarks(X.to(DEV), 40, start_idx=0)
+    np.testing.assert_array_equal(L.cpu().numpy(), flood_oracle.generate_landmarks(X.numpy(), 40, 0))
+    for kwargs in ({"points_per_edge": 30}, {"points_per_edge": None, "num_rand": 100}):
+        seed_all(9)
+        got = fb.flood_complex(X.to(DEV), L, **kwargs)
+        seed_all(9)
+        want = flood_oracle.flood_complex(X.numpy(), L.cpu().numpy(), **kwargs)
+        assert len(got) == 40 + 39
+        assert_close_dict(got, want, rtol=RTOL, atol=ATOL, what=str(kwargs))
+
+
+def test_gudhi_branch_end_to_end(monkeypatch):
+    """flood_complex with a gudhi module present (the oracle's stand-in injected, gudhi itself is
+    not in the image): Delaunay step and container are "gudhi's", values equal the default path
+    (reference flooder/core.py:130-132, 278-288)."""
+    import types
+
+    from flooder_b200 import simplex_tree as st
+    from oracle import simplex_tree as ost
+
+    seed_all(10)
+    X = fb.generate_noisy_torus_points_3d(8000).to(DEV)
+    L = fb.generate_landmarks(X, 60, start_idx=0)
+    plain = {kw: fb.flood_complex(X, L, **dict(kw)) for kw in
+             ((("points_per_edge", 9),), (("points_per_edge", None), ("num_rand", 50), ("max_dimension", 2)))}
+    g = types.ModuleType("gudhi")
+    g.DelaunayComplex, g.SimplexTree = ost.DelaunayComplex, ost.DictSimplexTree
+    monkeypatch.setattr(st, "_gudhi", g)
+    monkeypatch.setattr(st, "HAS_GUDHI", True)
+    for kw, want in plain.items():
+        torch.manual_seed(11)
+        tree = fb.flood_complex(X, L, return_simplex_tree=True, **dict(kw))
+        assert isinstance(tree, ost.DictSimplexTree)
+        torch.manual_seed(11)
+        got = fb.flood_complex(X, L, **dict(kw))
+        assert set(got) == set(want)
+        if dict(kw).get("num_rand") is None:                 # random mode draws fresh weights per call
+            for s, v in want.items():
+                assert got[s] == v or (np.isnan(v) and np.isnan(got[s])), s
+            assert dict((tuple(s), f) for s, f in tree.get_simplices()) == got
+
+
+def test_memory_bounded_slabs(monkeypatch):
+    """The (S, R) per-sample buffer is processed in slabs when it would not fit (the role of the
+    reference's batch_size, flooder/core.py:193-226): same bits."""
+    seed_all(12)
+    X = fb.generate_noisy_torus_points_3d(20_000).to(DEV)
+    L = fb.generate_landmarks(X, 80, start_idx=0)
+    want = fb.flood_complex(X, L, points_per_edge=10)
+    monkeypatch.setenv("FLOODER_B200_SLAB_BYTES", str(37 * 220 * 4))      # 37 simplices per slab
+    got = fb.flood_complex(X, L, points_per_edge=10)
+    assert got == want
+
+
+def test_float64_landmarks_triangulated_in_float64():
+    """Landmarks are handed to the Delaunay step in the precision they come in (the reference
+    passes its landmark tensor to gudhi as is)."""
+    seed_all(13)
+    X = torch.rand(4000, 2, dtype=torch.float64)
+    L = X[:50].clone()
+    with pytest.warns(RuntimeWarning):
+        got = fb.flood_complex(X.to(DEV), L.to(DEV), points_per_edge=8)
+    want = flood_oracle.flood_complex(X.numpy(), L.numpy(), points_per_edge=8)
+    assert_close_dict(got, want, rtol=RTOL, atol=3e-6)

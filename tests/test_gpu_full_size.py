@@ -98,3 +98,172 @@ def test_work_count_full_size(torus_1m):
     x = native.sample_points(w.cpu().numpy(), verts[sel[:4]].cpu().numpy())
     ref = native.min_dist(pts.numpy(), x, c[sel[:4]].cpu().numpy(), r[sel[:4]].cpu().numpy())
     np.testing.assert_array_equal(np.sqrt(md2[sel[:4]].cpu().numpy()), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: two-sided parity at BASELINE.json's sizes
+# ------------------------------------------------------------------------------------------
+RTOL, ATOL = 1e-5, 1e-7
+
+
+def _oracle_cell_values(tree, lms, cells, ppe, dim):
+    """Per-cell face values of the reference CPU path (flooder/core.py:188, 197-199, 251-257):
+    exact KD-tree distances (float64) of the float32 sample points, maximum per face.  Column
+    ``m - 1`` belongs to the face made of the vertex positions set in ``m`` (the layout of
+    ``flood_face_max_f32``).  All host threads (the reference uses one; same numbers)."""
+    weights, vertex_idxs, face_idxs = flood_oracle.generate_grid(ppe, dim)
+    out = np.empty((len(cells), 2 ** (dim + 1) - 1))
+    step = max(1, 4_000_000 // weights.shape[0])             # bounded memory: ~4 M sample points per query
+    for lo in range(0, len(cells), step):
+        x = flood_oracle.sample_points(weights, lms[cells[lo:lo + step]])
+        dist, _ = tree.query(x.reshape(-1, dim), workers=-1)
+        dist = dist.reshape(x.shape[0], x.shape[1])
+        for rows, vsel in zip(face_idxs, vertex_idxs):
+            for j in range(rows.shape[0]):
+                col = sum(1 << int(k) for k in vsel[j]) - 1
+                out[lo:lo + step, col] = dist[:, rows[j]].max(axis=1)
+    return out
+
+
+def _assert_two_sided(got, want, what):
+    err = np.abs(got - want)
+    tol = ATOL + RTOL * np.abs(want)
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.size} values off; worst |diff| {err.max():.3e} "
+                           f"(rel {np.max(err / np.maximum(np.abs(want), 1e-30)):.3e})")
+    return float(err.max()), float(np.max(err / np.maximum(np.abs(want), 1e-12)))
+
+
+def _full_job(kind, record):
+    """Every simplex of a 1 M-point / 1 k-landmark job against the oracle, both sides."""
+    from scipy.spatial import KDTree
+
+    from flooder_b200 import core
+    from flooder_b200.simplex_tree import FaceTable
+
+    seed_all()
+    if kind == "torus":
+        pts = fb.generate_noisy_torus_points_3d(1_000_000)
+    else:
+        pts = fb.generate_swiss_cheese_points(1_000_000, (0, 0, 0), (1, 1, 1), 6, (0.1, 0.2))[0].cpu()
+    dev = pts.to(DEV)
+    lms_dev = dev[fb.fps_indices(dev, 1000, 0)]
+    host, lms = pts.numpy(), lms_dev.cpu().numpy()
+    cells = delaunay_cells(lms)
+    S = len(cells)
+
+    # (1) per-cell values, two-sided: the GPU's (S, 15) matrix against per-cell KD-tree maxima on
+    #     bit-identical sample points
+    cloud = core.PreparedCloud(dev)
+    verts = lms_dev[torch.as_tensor(cells, device=DEV)]
+    got_cells = core.covering_values(cloud, verts, core._grid_weights(30, 3, DEV), grid_mode=True).cpu().numpy()
+    want_cells = _oracle_cell_values(KDTree(host), lms, cells, 30, 3)
+    worst_abs, worst_rel = _assert_two_sided(got_cells.astype(np.float64), want_cells, f"{kind} per-cell values")
+
+    # (2) the scatter: flood_complex keeps, for a face shared by several cells, the smallest of the
+    #     per-coface values (the reference keeps the last one written, core.py:258-268)
+    fc = fb.flood_complex(dev, lms_dev)
+    table = FaceTable(cells, n_vertices=1000)
+    n_simplices = 0
+    for k, combos in table.combos.items():
+        cols = [sum(1 << p for p in combo) - 1 for combo in combos]
+        best = np.full(len(table.faces[k]), np.inf)
+        np.minimum.at(best, table.cell_face[k].reshape(-1), got_cells[:, cols].astype(np.float64).reshape(-1))
+        got = np.array([fc[tuple(f)] for f in table.faces[k].tolist()])
+        np.testing.assert_array_equal(got, best)
+        n_simplices += len(best)
+        # ... and every simplex of the complex against the oracle, two-sided: the oracle's value
+        # for a shared face is one of its cofaces' values (whichever the reference writes last);
+        # the GPU value must lie between the smallest and the largest of them
+        lo = np.full(len(best), np.inf)
+        hi = np.full(len(best), -np.inf)
+        np.minimum.at(lo, table.cell_face[k].reshape(-1), want_cells[:, cols].reshape(-1))
+        np.maximum.at(hi, table.cell_face[k].reshape(-1), want_cells[:, cols].reshape(-1))
+        assert (got >= lo - (ATOL + RTOL * lo)).all() and (got <= hi + (ATOL + RTOL * hi)).all()
+        # cofaces evaluate a shared face on sample points that differ by float32 rounding of
+        # `weights @ vertices` only (SURVEY.md section 7, "shared faces"): the spread is noise
+        assert np.max(hi - lo) <= 2e-6, f"{kind}: coface spread {np.max(hi - lo):.3e}"
+    assert n_simplices == len(fc)
+    record[kind] = dict(simplices=len(fc), cells=S, worst_abs=worst_abs, worst_rel=worst_rel)
+    return record[kind]
+
+
+@pytest.fixture(scope="module")
+def parity_record():
+    rec = {}
+    yield rec
+    # kept with the run's artefacts when the suite runs under gpurun (profiles/ is the tracked copy)
+    import json
+    import os
+
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if rec and os.path.isdir(out):
+        with open(os.path.join(out, "parity_full_size.json"), "w") as fh:
+            json.dump(rec, fh, indent=1)
+
+
+def test_torus_1m_every_simplex_two_sided(parity_record):
+    """north_star: flood_complex on the 1 M-point noisy torus / 1 k landmarks matches the
+    reference's filtration within 1e-5 -- all 24 889 simplices, both sides (BASELINE configs[1])."""
+    rec = _full_job("torus", parity_record)
+    assert rec["simplices"] > 24_000
+
+
+def test_cheese_1m_every_simplex_two_sided(parity_record):
+    """BASELINE configs[2] (examples/example_01_cheese_3d.py shape): 1 M-point swiss cheese."""
+    _full_job("cheese", parity_record)
+
+
+def _sampled_job(name, pts, n_lms, ppe, n_random, record):
+    """Big jobs: the 20 largest balls + n_random random cells, per-cell values two-sided, and the
+    kernel's candidate counts of the largest balls against the plain-C ball count."""
+    from scipy.spatial import KDTree
+
+    from flooder_b200 import core
+
+    dim = pts.shape[1]
+    dev = pts.to(DEV)
+    cloud = core.PreparedCloud(dev)
+    lms_dev = dev[fb.fps_indices(dev, n_lms, 0, cloud=cloud)]
+    host, lms = pts.numpy(), lms_dev.cpu().numpy()
+    cells = delaunay_cells(lms)
+    ext = _native.ext()
+    verts_all = lms_dev[torch.as_tensor(cells, device=DEV)].contiguous()
+    _c, radii = ext.bounding_balls(verts_all)
+    largest = torch.argsort(radii, descending=True)[:20].cpu().numpy()
+    rng = np.random.default_rng(0)
+    sel = np.unique(np.concatenate([largest, rng.choice(len(cells), size=n_random, replace=False)]))
+    w = core._grid_weights(ppe, dim, DEV)
+    got, det = core.covering_values(cloud, verts_all[torch.as_tensor(sel, device=DEV)].contiguous(), w,
+                                    grid_mode=True, return_details=True)
+    want = _oracle_cell_values(KDTree(host), lms, cells[sel], ppe, dim)
+    worst_abs, worst_rel = _assert_two_sided(got.cpu().numpy().astype(np.float64), want, f"{name} per-cell values")
+    # heavy tail: balls that swallow most of the cloud (chunks split over many CTAs)
+    pos = np.searchsorted(sel, largest)
+    cnt = det["cand_count"].cpu().numpy()[pos]
+    want_cnt = native.ball_counts(host, det["centers"].cpu().numpy()[pos], det["radii"].cpu().numpy()[pos])
+    np.testing.assert_array_equal(cnt, want_cnt)
+    assert int(det["evals"].item()) == int(det["cand_count"].sum().item()) * w.shape[0]
+    record[name] = dict(cells=len(cells), checked_cells=len(sel), largest_ball_points=int(want_cnt.max()),
+                        n_points=len(host), worst_abs=worst_abs, worst_rel=worst_rel)
+    # the whole job through the public API: a filtered complex over the same cells
+    if dim <= 3:
+        fc = fb.flood_complex(dev, lms_dev, points_per_edge=ppe)
+        for row, cell in zip(got.cpu().numpy(), cells[sel]):
+            assert fc[tuple(int(v) for v in cell)] == row[-1]          # top cell: column 2^K - 2
+        record[name]["simplices"] = len(fc)
+
+
+def test_gauss_10m_5k_sampled_two_sided(parity_record):
+    """BASELINE configs[3]: standard Gaussian, 10 M points, 5 k landmarks (31.5 k cells; balls of up
+    to 1.6 M points)."""
+    seed_all()
+    _sampled_job("gauss_10m_5k", torch.randn(10_000_000, 3), 5000, 30, 600, parity_record)
+    assert parity_record["gauss_10m_5k"]["largest_ball_points"] > 1_000_000
+
+
+def test_uniform_5d_2m_2k_sampled_two_sided(parity_record):
+    """BASELINE configs[4]: uniform 5-D cloud, 2 M points, 2 k landmarks, 6 points per edge (the
+    largest lattice the reference can hold in 5-D)."""
+    seed_all()
+    _sampled_job("uniform5d_2m_2k_ppe6", torch.rand(2_000_000, 5), 2000, 6, 600, parity_record)

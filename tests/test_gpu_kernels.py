@@ -119,17 +119,17 @@ def test_fps_duplicates(ext):
 # ------------------------------------------------------------------------------------------
 # bounding balls
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d,K", [(2, 3), (3, 4), (3, 2), (3, 1), (5, 6)])
+@pytest.mark.parametrize("d,K", [(2, 3), (3, 4), (3, 2), (3, 1), (5, 6), (8, 9), (1, 2), (6, 4)])
 def test_bounding_balls(ext, d, K):
     pts = _cloud("gauss", 500, d, seed=d * 10 + K)
     g = torch.Generator().manual_seed(1)
-    verts = pts[torch.randint(0, 500, (300, K), generator=g)]
+    verts = pts[torch.randint(0, 500, (3000, K), generator=g)]
     c, r = ext.bounding_balls(verts.cuda().contiguous())
     c0, r0 = flood_oracle.bounding_balls(verts.numpy(), K - 1)
-    np.testing.assert_allclose(r.cpu().numpy(), r0, rtol=1e-6, atol=1e-7)
-    # centres may differ only where two edges tie for the longest within rounding
-    same = np.isclose(c.cpu().numpy(), c0, rtol=0, atol=1e-6).all(axis=1)
-    assert same.mean() > 0.99
+    # bit-exact: same operation sequence, first maximum of the flattened K x K matrix wins
+    # (the random vertex picks contain repeated vertices, i.e. exact ties between edges)
+    np.testing.assert_array_equal(c.cpu().numpy(), c0)
+    np.testing.assert_array_equal(r.cpu().numpy(), r0)
 
 
 # ------------------------------------------------------------------------------------------
