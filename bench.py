@@ -10,19 +10,28 @@ One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement")
   reference bounding ball) squared distance + running-min update; the algorithmic count
   E = sum_s R * |ball(s) & cloud| is produced by the kernel's own counter and does not depend
   on tiling or padding.
-* step = one pass of the device path over the whole job: cloud grid build, bounding balls,
-  covering-radius kernel, per-face maxima (and the NCCL all-gather of the per-simplex values
-  when N > 1); the simplex list is sharded over the N ranks, the cloud is replicated
-  (strong scaling: the job is fixed).
-* value = E * K / (sum of the K per-step device times, CUDA events, max over ranks).
-* e2e = the same metric through the public API: pinned-host cloud -> device copy +
+* step = one pass of the device path of flood_complex over the whole job, enqueued by the same
+  function the product calls (flooder_b200.core.device_pass, after the cloud build): cell grid,
+  bounding balls, covering-radius kernel, per-face maxima (and, when N > 1, cost plan, partition
+  and the NCCL all-gather of the per-simplex values); the simplex list is sharded over the N
+  ranks, the cloud is replicated (strong scaling: the job is fixed).
+* value / ms_per_step / roofline: the step with EVERY evaluation executed (library option
+  prune=0), i.e. the kernel whose executed work equals E; roofline = FP32 issue slots of the
+  direct-difference form, 2D+1 = 7 per evaluation, peak = SMs x 128 lanes x
+  max SM clock.
+* default_path: the same step as the product runs it by default -- the sweep is pruned EXACTLY
+  (bit-identical minima, tests/test_gpu_kernels.py::test_pruning_is_exact): executed_frac of E is
+  evaluated; algorithmic_speedup = exhaustive step time / default step time.
+* e2e = the metric through the public API with host buffers: pinned-host cloud -> device copy +
   flood_complex(points, n_landmarks) (FPS, host Delaunay, kernels, device->host read of the
-  values, assembly of the complex), wall clock with synchronisation on both sides.
-* roofline: FP32 issue slots of the direct-difference form, 2D+1 = 7 per evaluation
-  (SURVEY.md section 8d); peak = SMs x 128 lanes x max SM clock.
-* cpu_baseline / --impl reference: the reference's CPU path (exact KD-tree nearest neighbour
-  per sample point, scipy, one thread as in the reference) restated in oracle/, timed on a
-  bounded sample of the same job's simplices.
+  values, assembly of the complex), wall clock with synchronisation on both sides; default
+  (pruned) path, the exhaustive figure beside it.
+* cpu_baseline / --impl reference: the reference's CPU path (exact KD-tree nearest neighbour per
+  sample point, scipy) restated in oracle/, timed on a bounded sample of the same job's simplices
+  with all host threads; plus the UNMODIFIED reference (baseline/_ref, gudhi/fpsample stand-ins)
+  on BASELINE configs[0] (torus 10 k / 100 landmarks), where the whole job fits.
+* gpu_reference (N = 1): the unmodified reference's own Triton path on the same GPU and inputs.
+* configs (N = 1; gauss_10m_5k also sharded at N > 1): the other BASELINE.json configurations.
 """
 from __future__ import annotations
 
@@ -43,13 +52,15 @@ if ROOT not in sys.path:
 METRIC = "point-simplex distance evaluations/s (flood_complex, noisy torus 1M pts, 1k landmarks, 3D)"
 UNIT = "evals/s"
 WORKLOADS = {
-    # name: (generator, n_points, n_landmarks, dim, points_per_edge)
-    "torus_1m_1k": ("torus", 1_000_000, 1000, 3, 30),
-    "torus_10k_100": ("torus", 10_000, 100, 3, 30),
-    "gauss_10m_5k": ("gauss", 10_000_000, 5000, 3, 30),
+    # name: (generator, n_points, n_landmarks, dim, points_per_edge, description)
+    "torus_1m_1k": ("torus", 1_000_000, 1000, 3, 30, "noisy torus 1000000 points, 1000 landmarks, 3D (BASELINE.json configs[1])"),
+    "torus_10k_100": ("torus", 10_000, 100, 3, 30, "noisy torus 10000 points, 100 landmarks, 3D (BASELINE.json configs[0])"),
+    "cheese_1m_1k": ("cheese", 1_000_000, 1000, 3, 30, "swiss cheese 1000000 points, 1000 landmarks, 3D (BASELINE.json configs[2])"),
+    "gauss_10m_5k": ("gauss", 10_000_000, 5000, 3, 30, "standard Gaussian 10000000 points, 5000 landmarks, 3D (BASELINE.json configs[3])"),
+    "uniform5d_2m_2k_ppe6": ("uniform", 2_000_000, 2000, 5, 6, "uniform 5D 2000000 points, 2000 landmarks, 6 points per edge (BASELINE.json configs[4])"),
 }
-KERNELS_PER_STEP = 13  # cloud build 6, balls 1, covering 5 (fill, plan, scan, eval seed + full), face max 1 (+1 plan when sharded)
-SLOTS_PER_EVAL = {2: 5, 3: 7, 4: 9, 5: 11, 6: 13}
+EXTRA_CONFIGS = ["cheese_1m_1k", "gauss_10m_5k", "uniform5d_2m_2k_ppe6"]
+SLOTS_PER_EVAL = {1: 3, 2: 5, 3: 7, 4: 9, 5: 11, 6: 13, 7: 15, 8: 17}
 
 
 def make_cloud(kind: str, n: int, dim: int):
@@ -61,8 +72,12 @@ def make_cloud(kind: str, n: int, dim: int):
     np.random.seed(42)
     if kind == "torus":
         return fb.generate_noisy_torus_points_3d(n)
+    if kind == "cheese":
+        return fb.generate_swiss_cheese_points(n, (0,) * dim, (1,) * dim, 6, (0.1, 0.2))[0].cpu()
     if kind == "gauss":
         return torch.randn(n, dim)
+    if kind == "uniform":
+        return torch.rand(n, dim)
     raise ValueError(kind)
 
 
@@ -121,166 +136,203 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference's CPU path)
+# CPU arms (oracle port of the reference's CPU path; the unmodified reference on configs[0])
 # --------------------------------------------------------------------------------------------
 def cpu_reference_sample(points: np.ndarray, simplex_vertices: np.ndarray, weights: np.ndarray,
-                         cand_counts: np.ndarray, tree=None, workers: int = 1):
-    """Time the reference's CPU distance step (flooder/core.py:197-199: one KDTree.query over all
-    sample points, float64) on the given simplices; returns (seconds, evaluations, tree)."""
-    from scipy.spatial import KDTree
-
+                         cand_counts: np.ndarray, tree, workers: int):
+    """Time the reference's CPU distance step (flooder/core.py:188, 197-199: sample points, one
+    KDTree.query over all of them, float64) on the given simplices; returns (seconds, evaluations)."""
     from oracle import flood_oracle
 
-    if tree is None:
-        tree = KDTree(points)
     t0 = time.perf_counter()
     x = flood_oracle.sample_points(weights, simplex_vertices)             # core.py:188
     dist, _ = tree.query(x.reshape(-1, x.shape[-1]), workers=workers)     # core.py:197-199
     _ = dist.reshape(x.shape[0], x.shape[1]).max(axis=1)
     dt = time.perf_counter() - t0
     evals = int(cand_counts.sum()) * weights.shape[0]
-    return dt, evals, tree
+    return dt, evals
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU path on the host cores, rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_config1():
+    """The UNMODIFIED reference (baseline/_ref/flooder/core.py, CPU path) on BASELINE configs[0]:
+    noisy torus 10 k points / 100 landmarks, whole job, with the gudhi/fpsample stand-ins."""
+    from oracle import flood_oracle, ref_shims
+
+    try:
+        fl = ref_shims.import_reference(os.path.join(ROOT, "baseline", "_ref"))
+    except ImportError as exc:
+        return {"unavailable": str(exc)}
     import torch
+
+    kind, n, n_lms, dim, ppe, desc = WORKLOADS["torus_10k_100"]
+    pts = make_cloud(kind, n, dim)
+    fl.flood_complex(pts[:2000], 20, points_per_edge=5)          # warm-up: lazy imports (sympy via torch)
+    t0 = time.perf_counter()
+    lms = fl.generate_landmarks(pts, n_lms, start_idx=0)
+    t_fps = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = fl.flood_complex(pts, lms, points_per_edge=ppe)
+    wall = time.perf_counter() - t0
+    E = flood_oracle.algorithmic_evals(pts.numpy(), lms.numpy(), points_per_edge=ppe)
+    return {"kind": "_ref", "workload": desc, "value": E / wall, "unit": UNIT, "cores": 1,
+            "flood_complex_wall_s": wall, "landmark_fps_s": t_fps, "evals": E, "simplices": len(res),
+            "note": "unmodified reference core.py (CPU path: scipy KDTree.query, single thread as the reference "
+                    "calls it) from baseline/_ref with the gudhi/fpsample stand-ins of oracle/ref_shims.py; whole job"}
+
+
+def cpu_arm(workload: str, per_step: int, steps: int, warmup: int, threads: int = -1):
+    """Oracle port of the reference CPU path on bounded samples of the workload's simplices."""
+    from scipy.spatial import KDTree
 
     from oracle import flood_oracle, native
     from oracle.simplex_tree import delaunay_top_simplices
 
-    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
+    kind, n, n_lms, dim, ppe, desc = WORKLOADS[workload]
     pts = make_cloud(kind, n, dim).numpy()
+    t0 = time.perf_counter()
     lms = pts[native.fps(pts, n_lms, 0)]
+    fps_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
     cells = delaunay_top_simplices(lms)
+    delaunay_s = time.perf_counter() - t0
     weights, _, _ = flood_oracle.generate_grid(ppe, dim)
-    rng = np.random.default_rng(0)
-    per_step = args.ref_simplices_per_step
-    order = rng.permutation(len(cells))
     verts_all = lms[cells]
     centers, radii = flood_oracle.bounding_balls(verts_all, dim)
-    from scipy.spatial import KDTree
-
     t0 = time.perf_counter()
     tree = KDTree(pts)                                                    # core.py:128
     build_s = time.perf_counter() - t0
+    order = np.random.default_rng(0).permutation(len(cells))
     times, evals = [], []
-    for step in range(args.warmup + args.steps):
+    for step in range(warmup + steps):
         sel = order[(step * per_step) % len(cells):][:per_step]
         counts = native.ball_counts(pts, centers[sel], radii[sel])
-        dt, ev, _ = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree=tree, workers=1)
-        if step >= args.warmup:
+        dt, ev = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree, threads)
+        if step >= warmup:
             times.append(dt)
             evals.append(ev)
-    total_t, total_e = float(np.sum(times)), float(np.sum(evals))
-    value = total_e / total_t
-    # one extra sample with every host thread, for context
     sel = order[:per_step]
     counts = native.ball_counts(pts, centers[sel], radii[sel])
-    dt_all, ev_all, _ = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree=tree, workers=-1)
-    sample = (f"{per_step} of {len(cells)} simplices per step (random, seeded), {weights.shape[0]} samples each, "
-              f"KD-tree over the full {n}-point cloud built once outside the steps ({build_s:.2f} s)")
+    dt1, ev1 = cpu_reference_sample(pts, verts_all[sel], weights, counts, tree, 1)
+    total_t, total_e = float(np.sum(times)), float(np.sum(evals))
+    frac = per_step / len(cells)
+    one_off = build_s + fps_s + delaunay_s
+    return {
+        "value": total_e / total_t, "unit": UNIT, "cores": os.cpu_count() if threads < 0 else threads, "kind": "port",
+        "sample": f"{per_step} of {len(cells)} simplices per step (random, seeded), {weights.shape[0]} samples each; "
+                  f"{steps} timed steps after {warmup} warm-up; scipy KDTree.query(workers=-1) over a tree of the full "
+                  f"{n}-point cloud",
+        "host_cores": os.cpu_count(),
+        "value_single_thread": ev1 / dt1,
+        "note": "the reference calls KDTree.query without workers= (one thread, value_single_thread); value uses "
+                "every host thread",
+        "one_off_seconds": {"kdtree_build": build_s, "landmark_fps_scalar_c": fps_s, "delaunay_qhull": delaunay_s},
+        "ms_per_step": 1e3 * total_t / max(1, steps),
+        "e2e_value": total_e / (total_t + steps * frac * one_off),
+        "projected_full_job_s": one_off + (total_t / max(1, steps)) / frac,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    arm = cpu_arm(args.workload, args.ref_simplices_per_step, args.steps, args.warmup)
+    cpu = {k: arm[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores", "value_single_thread",
+                                "note", "one_off_seconds", "projected_full_job_s")}
+    if not args.no_ref_config1:
+        cpu["reference_config1"] = reference_config1()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
+        "impl": "reference", "metric": METRIC, "value": arm["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": arm["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args, None),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count(),
-                         "value_all_host_threads": ev_all / dt_all,
-                         "note": "reference calls scipy KDTree.query without workers= (single thread); "
-                                 "value_all_host_threads uses workers=-1"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "data": "synthetic", "config": config_dict(args.workload, args.gpus, None),
+        "cpu_baseline": cpu,
+        "e2e": {"value": arm["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "distance step plus the sample's proportional share of the one-off host work (KD-tree build, "
+                        "landmark FPS, Delaunay)"},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_reference_triton(args):
-    """--impl reference_triton (informative, not part of the driver contract): the UNMODIFIED
-    reference package installed under baseline/_ref, its own Triton path on this GPU
+# --------------------------------------------------------------------------------------------
+# the reference's own GPU path (Triton) on this GPU
+# --------------------------------------------------------------------------------------------
+def reference_triton(workload: str, runs: int = 3):
+    """The UNMODIFIED reference package from baseline/_ref, its own Triton path on this GPU
     (flooder/core.py:193-226 with batch_size=64 as in examples/example_02_torus_3d.py), with the
-    gudhi/fpsample stand-ins of oracle/ref_shims.py.  Rank 0 only."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+    gudhi/fpsample stand-ins of oracle/ref_shims.py.  Returns a dict (or {"unavailable": why})."""
     import torch
 
     from oracle import ref_shims
 
-    ref_root = os.path.join(ROOT, "baseline", "_ref")
     try:
-        fl = ref_shims.import_reference(ref_root)
+        fl = ref_shims.import_reference(os.path.join(ROOT, "baseline", "_ref"))
     except ImportError as exc:
-        print(json.dumps({"impl": "reference_triton", "unavailable": str(exc)}), flush=True)
-        return
-    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
-    pts = make_cloud(kind, n, dim)
-    dev = torch.device("cuda")
-    lms = fl.generate_landmarks(pts, n_lms, start_idx=0).to(dev)
-    dpts = pts.to(dev)
-    # instrument the two Triton entry points to split out kernel time and count the work
-    core = fl.core
-    stats = {"mask_ms": 0.0, "filt_ms": 0.0, "nonzero_ms": 0.0, "cand": 0}
-    orig_mask, orig_filt = core.compute_mask, core.compute_filtration
+        return {"unavailable": str(exc)}
+    kind, n, n_lms, dim, ppe, desc = WORKLOADS[workload]
+    try:
+        pts = make_cloud(kind, n, dim)
+        dev = torch.device("cuda")
+        lms = fl.generate_landmarks(pts, n_lms, start_idx=0).to(dev)
+        dpts = pts.to(dev)
+        core = fl.core
+        stats = {"mask_ms": 0.0, "filt_ms": 0.0, "cand": 0}
+        orig_mask, orig_filt = core.compute_mask, core.compute_filtration
 
-    def timed(fn, key):
-        def wrapper(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = fn(*a, **k)
-            e1.record()
-            e1.synchronize()
-            stats[key] += e0.elapsed_time(e1)
+        def timed(fn, key):
+            def wrapper(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                e1.record()
+                e1.synchronize()
+                stats[key] += e0.elapsed_time(e1)
+                return out
+            return wrapper
+
+        fl.flood_complex(dpts[:10000], lms, use_triton=True, points_per_edge=ppe)   # warm-up as in the examples
+        torch.cuda.synchronize()
+        walls = []
+        for _ in range(runs):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+
+        def mask_counting(points, centers, radii, *rest):     # instrumented pass: kernel split + work count
+            out = timed(orig_mask, "mask_ms")(points, centers, radii, *rest)
+            stats["cand"] += int(out[:, : points.shape[0]].sum().item())
             return out
-        return wrapper
 
-    fl.flood_complex(dpts[:10000], lms, use_triton=True, points_per_edge=ppe)   # warm-up as in the examples
-    torch.cuda.synchronize()
-    walls = []
-    for _ in range(max(1, min(args.steps, 3))):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
-        torch.cuda.synchronize()
-        walls.append(time.perf_counter() - t0)
-    # instrumented pass (kernel split + algorithmic work count)
-    def mask_counting(points, centers, radii, *rest):
-        out = timed(orig_mask, "mask_ms")(points, centers, radii, *rest)
-        stats["cand"] += int(out[:, : points.shape[0]].sum().item())
-        return out
-    core.compute_mask = mask_counting
-    core.compute_filtration = timed(orig_filt, "filt_ms")
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
-    torch.cuda.synchronize()
-    instrumented_wall = time.perf_counter() - t0
-    core.compute_mask, core.compute_filtration = orig_mask, orig_filt
+        core.compute_mask = mask_counting
+        core.compute_filtration = timed(orig_filt, "filt_ms")
+        try:
+            fl.flood_complex(dpts, lms, batch_size=64, use_triton=True, points_per_edge=ppe)
+            torch.cuda.synchronize()
+        finally:
+            core.compute_mask, core.compute_filtration = orig_mask, orig_filt
+    except Exception as exc:  # noqa: BLE001  (the reference arm must not take the benchmark down)
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     from math import comb
 
-    R = comb(ppe + dim - 1, dim)
-    E = stats["cand"] * R
+    E = stats["cand"] * comb(ppe + dim - 1, dim)
     wall = float(np.median(walls))
-    print(json.dumps({
-        "impl": "reference_triton", "metric": METRIC, "value": E / (stats["filt_ms"] * 1e-3), "unit": UNIT,
-        "n_gpus": 1, "config": config_dict(args, {"batch_size": 64, "evals_per_step": E, "simplices_returned": len(res)}),
-        "e2e": {"value": E / wall, "unit": UNIT, "flood_complex_wall_s": wall, "walls": walls},
+    return {
+        "impl": "reference Triton path (unmodified, baseline/_ref), batch_size=64", "workload": desc,
+        "kernel_evals_per_s": E / (stats["filt_ms"] * 1e-3), "evals": E,
         "kernel_ms": {"compute_filtration": stats["filt_ms"], "compute_mask": stats["mask_ms"]},
-        "instrumented_wall_s": instrumented_wall,
-        "note": "value = E / time inside the reference's compute_filtration Triton kernel; e2e = E / flood_complex "
-                "wall on device-resident inputs (landmarks precomputed), median of the listed runs",
-    }), flush=True)
+        "flood_complex_wall_s": wall, "walls": walls, "e2e_evals_per_s": E / wall, "simplices": len(res),
+        "note": "kernel_evals_per_s = E / time inside the reference's compute_filtration kernel (CUDA events, "
+                "instrumented pass); flood_complex_wall_s = device-resident inputs, landmarks precomputed, median",
+    }
 
 
-def config_dict(args, extra):
-    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
-    cfg = {"workload": f"noisy torus {n} points, {n_lms} landmarks, {dim}D (BASELINE.json configs[1])"
-           if args.workload == "torus_1m_1k" else args.workload,
-           "n_points": n, "n_landmarks": n_lms, "dim": dim, "points_per_edge": ppe,
-           "parallelism": f"simplices sharded over {args.gpus} GPU(s), cloud replicated",
+def config_dict(workload, gpus, extra):
+    kind, n, n_lms, dim, ppe, desc = WORKLOADS[workload]
+    cfg = {"workload": desc, "n_points": n, "n_landmarks": n_lms, "dim": dim, "points_per_edge": ppe,
+           "parallelism": f"simplices sharded over {gpus} GPU(s), cloud replicated",
            "l2": "flushed between timed steps (256 MiB write)"}
     if extra:
         cfg.update(extra)
@@ -290,22 +342,103 @@ def config_dict(args, extra):
 # --------------------------------------------------------------------------------------------
 # the CUDA arm
 # --------------------------------------------------------------------------------------------
+class Job:
+    """One workload resident on this rank's GPU: cloud, landmarks (FPS), Delaunay cells, weights."""
+
+    def __init__(self, workload, dev, rank, world):
+        import torch
+
+        import flooder_b200 as fb
+        from flooder_b200 import core
+        from flooder_b200 import distributed as fdist
+        from flooder_b200.simplex_tree import delaunay_cells
+
+        self.kind, self.n, self.n_lms, self.dim, self.ppe, self.desc = WORKLOADS[workload]
+        self.workload, self.dev, self.rank, self.world = workload, dev, rank, world
+        self.host_pts = make_cloud(self.kind, self.n, self.dim).pin_memory()
+        self.pts = self.host_pts.to(dev, non_blocking=True)
+        self.lms = self.pts[fb.fps_indices(self.pts, self.n_lms, 0)]
+        t0 = time.perf_counter()
+        self.cells = delaunay_cells(self.lms.cpu().numpy())
+        self.delaunay_s = time.perf_counter() - t0
+        self.S = len(self.cells)
+        self.verts = self.lms[torch.as_tensor(self.cells, device=dev)].contiguous()
+        self.weights = core._grid_weights(self.ppe, self.dim, dev)
+        self.R, self.K = self.weights.shape
+        self.shard = fdist.Shard(rank, world) if world > 1 else None
+
+    def device_step(self, stats=None):
+        """The device path of one flood_complex call, through the product's own functions."""
+        from flooder_b200 import core
+
+        cloud = core.PreparedCloud(self.pts)
+        return core.device_pass(cloud, self.verts, self.weights, True, self.shard, stats)
+
+
+def timed_steps(job, steps, flush, barrier):
+    """K timed device steps (CUDA events, L2 flushed before each); returns (per-step ms list, the
+    last step's evals / executed counters of this rank)."""
+    import torch
+
+    out, stats = [], {}
+    for _ in range(steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        job.device_step(stats)
+        b.record()
+        b.synchronize()
+        out.append(a.elapsed_time(b))
+    barrier()
+    return out, int(stats["evals"].item()), int(stats["executed"].item())
+
+
+def measure_job(job, ext, steps, warmup, flush, barrier, reduce_max, reduce_sum, sm_count, sm_max_mhz):
+    """Exhaustive and default (pruned) timed regions for one job; returns the result dict."""
+    slots = SLOTS_PER_EVAL[job.dim]
+    peak_slots = sm_count * 128 * sm_max_mhz * 1e6
+    res = {}
+    for mode, prune in (("exhaustive", 0), ("default", -1)):
+        ext.set_option("prune", prune)
+        for _ in range(warmup):
+            job.device_step()
+            flush.fill_(1)
+        barrier()
+        ext.kernel_ms("cover_eval", True)
+        ext.kernel_ms("cover_seed", True)
+        ext.launch_count(True)
+        ms, evals_local, executed_local = timed_steps(job, steps, flush, barrier)
+        launches = ext.launch_count(True)
+        eval_total, eval_n = ext.kernel_ms("cover_eval", True)
+        seed_total, seed_n = ext.kernel_ms("cover_seed", True)
+        total_ms = reduce_max(float(np.sum(ms)))
+        E = reduce_sum(float(evals_local))
+        executed = reduce_sum(float(executed_local))
+        kernel_ms = reduce_max(eval_total / max(1, eval_n))
+        res[mode] = {"ms_per_step": total_ms / steps, "evals_per_step": E, "executed_per_step": executed,
+                     "kernel_ms_per_launch": kernel_ms, "seed_ms_per_launch": seed_total / max(1, seed_n),
+                     "launches": int(reduce_sum(float(launches))), "evals_per_s": E / (total_ms / steps * 1e-3),
+                     "kernel_evals_per_s": (E / job.world) / (kernel_ms * 1e-3),
+                     "kernel_frac": (E / job.world) / (kernel_ms * 1e-3) * slots / peak_slots}
+    ext.set_option("prune", -1)
+    res["slots_per_eval"] = slots
+    res["peak_slots"] = peak_slots
+    return res
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
 
     import flooder_b200 as fb
     from flooder_b200 import _native
-    from flooder_b200 import distributed as fdist
-    from flooder_b200.core import _support_masks
-    from flooder_b200.simplex_tree import delaunay_cells
+    from flooder_b200 import core as fcore
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
@@ -315,149 +448,112 @@ def run_cuda(args):
     ext = _native.ext()
     ext.set_option("time_kernels", 1)
 
-    kind, n, n_lms, dim, ppe = WORKLOADS[args.workload]
-    host_pts = make_cloud(kind, n, dim).pin_memory()
-    pts = host_pts.to(dev, non_blocking=True)
-    lms = pts[ext.fps(pts, n_lms, 0)]
-    cells = delaunay_cells(lms.cpu().numpy())
-    S_total = len(cells)
-    verts_all = lms[torch.as_tensor(cells, device=dev)].contiguous()
-    weights, _, _ = fb.generate_grid(ppe, dim, dev)
-    support = _support_masks(weights)
-    R, K = weights.shape
-    shard = fdist.Shard(rank, world) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def device_step():
-        """The device path of one flood_complex call (what flooder_b200.core enqueues)."""
-        ws = ext.cloud_build(pts, 0)
-        c_all, r_all = ext.bounding_balls(verts_all)
-        if shard is not None:          # balance by the candidate-stream lengths, largest first
-            cost = ext.covering_plan(ws, n, dim, c_all, r_all).to(torch.float32)
-            parts = fdist.partition(cost, world)
-            mine = parts[rank]
-        else:
-            parts, mine = None, torch.argsort(r_all, descending=True)
-        verts, c, r = verts_all[mine].contiguous(), c_all[mine].contiguous(), r_all[mine].contiguous()
-        md2, cnt, ev, executed = ext.covering_radius(ws, n, dim, verts, weights, None, c, r)
-        vals = ext.face_max(md2, support, K)
-        if shard is not None:
-            vals = fdist.gather_rows(vals, parts, shard)
-        else:
-            vals = torch.empty_like(vals).index_copy_(0, mine, vals)
-        return vals, ev, executed
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        device_step()
-        flush.fill_(1)
+    def _reduce(value, op):
+        t = torch.tensor([value], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.item()
+
+    reduce_max = lambda v: _reduce(v, dist.ReduceOp.MAX)   # noqa: E731
+    reduce_sum = lambda v: _reduce(v, dist.ReduceOp.SUM)   # noqa: E731
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    job = Job(args.workload, dev, rank, world)
+    n, n_lms, dim, ppe = job.n, job.n_lms, job.dim, job.ppe
+
     # landmark FPS on its own (device time, rank 0 reports): HBM-side evidence for the second kernel
     ext.kernel_ms("fps", True)
     for _ in range(3):
-        ext.fps(pts, n_lms, 0)
+        fb.fps_indices(job.pts, n_lms, 0)
     torch.cuda.synchronize()
     fps_ms_total, fps_launches = ext.kernel_ms("fps", True)
-    barrier()
-    ext.kernel_ms("cover_eval", True)
+
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    step_ms, evals_local = [], 0
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        _, ev, executed = device_step()
-        b.record()
-        b.synchronize()
-        step_ms.append(a.elapsed_time(b))
-        evals_local = int(ev.item())
-        executed_local = int(executed.item())
-    barrier()
+    m = measure_job(job, ext, args.steps, args.warmup, flush, barrier, reduce_max, reduce_sum, sm_count, sm_max_mhz)
     wall_s = time.perf_counter() - wall0
     clock_info = clocks.stop() if rank == 0 else None
-    eval_ms_total, eval_launches = ext.kernel_ms("cover_eval", True)
-
-    # the same steps with the exhaustive sweep (every in-ball candidate is evaluated): this is the
-    # kernel the FP32 issue roofline describes; the default path above prunes exactly (DESIGN.md 3.1)
-    ext.set_option("prune", 0)
-    for _ in range(2):
-        device_step()
-    barrier()
-    ext.kernel_ms("cover_eval", True)
-    exh_ms = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        device_step()
-        b.record()
-        b.synchronize()
-        exh_ms.append(a.elapsed_time(b))
-    barrier()
-    exh_kernel_total, exh_launches = ext.kernel_ms("cover_eval", True)
-    ext.set_option("prune", -1)
-
-    total_ms = torch.tensor([float(np.sum(step_ms))], device=dev, dtype=torch.float64)
-    evals_t = torch.tensor([float(evals_local)], device=dev, dtype=torch.float64)
-    executed_t = torch.tensor([float(executed_local)], device=dev, dtype=torch.float64)
-    eval_ms_t = torch.tensor([eval_ms_total / max(1, eval_launches)], device=dev, dtype=torch.float64)
-    exh_t = torch.tensor([float(np.sum(exh_ms)), exh_kernel_total / max(1, exh_launches)], device=dev,
-                         dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
-        dist.all_reduce(executed_t, op=dist.ReduceOp.SUM)
-        dist.all_reduce(eval_ms_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(exh_t, op=dist.ReduceOp.MAX)
-    E = evals_t.item()                      # whole job, per step
-    ms_per_step = total_ms.item() / args.steps
-    value = E / (ms_per_step * 1e-3)
+    exh, dflt = m["exhaustive"], m["default"]
+    E = exh["evals_per_step"]
 
     # ---- end to end through the public API --------------------------------------------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    host_lms_bytes = n_lms * dim * 4
-    fb.flood_complex(host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        dpts = host_pts.to(dev, non_blocking=True)                      # H2D from pinned memory
-        res = fb.flood_complex(dpts, n_lms, points_per_edge=ppe)       # includes D2H of the values
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = e2e_t.item()
-    n_simplices = len(res)
-    # untimed diagnostic pass: per-stage seconds with a device sync after every stage
-    from flooder_b200 import core as fcore
+    def e2e_wall(steps, **env):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            fb.flood_complex(job.host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                dpts = job.host_pts.to(dev, non_blocking=True)                   # H2D from pinned memory
+                res = fb.flood_complex(dpts, n_lms, points_per_edge=ppe)        # includes D2H of the values
+            barrier()
+            return reduce_max((time.perf_counter() - t0) / steps), len(res)
+        finally:
+            for k in env:
+                del os.environ[k]
 
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_s, n_simplices = e2e_wall(e2e_steps)
+    ext.set_option("prune", 0)
+    e2e_exh_s, _ = e2e_wall(e2e_steps)
+    ext.set_option("prune", -1)
+    e2e_single_s = e2e_wall(e2e_steps, FLOODER_B200_NO_SHARD="1")[0] if world > 1 else e2e_s
+    # untimed diagnostic pass: per-stage seconds with a device sync after every stage
     fcore.PROFILE_STAGES = True
-    fb.flood_complex(host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)
+    fb.flood_complex(job.host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)
     fcore.PROFILE_STAGES = False
     stage_seconds = {k: round(v, 5) for k, v in fcore.last_stage_seconds.items()}
 
+    # ---- the other BASELINE configurations -----------------------------------------------------
+    configs = {}
+    if not args.no_configs:
+        names = EXTRA_CONFIGS if world == 1 else ["gauss_10m_5k"]
+        del job.verts, job.pts
+        for name in names:
+            torch.cuda.empty_cache()
+            cj = Job(name, dev, rank, world)
+            cm = measure_job(cj, ext, max(1, min(args.steps, args.config_steps)), 1, flush, barrier, reduce_max,
+                             reduce_sum, sm_count, sm_max_mhz)
+            entry = {"workload": cj.desc, "simplices": cj.S, "samples_per_simplex": int(cj.R),
+                     "evals_per_step": cm["exhaustive"]["evals_per_step"],
+                     "exhaustive": {k: cm["exhaustive"][k] for k in ("ms_per_step", "evals_per_s", "kernel_ms_per_launch")},
+                     "frac": cm["exhaustive"]["kernel_frac"],
+                     "default_path": {"ms_per_step": cm["default"]["ms_per_step"], "evals_per_s": cm["default"]["evals_per_s"],
+                                      "executed_frac": cm["default"]["executed_per_step"] / max(1.0, cm["default"]["evals_per_step"])},
+                     "host_delaunay_s": cj.delaunay_s}
+            if cj.dim <= 3:         # 5-D end to end is dominated by the host triangulation / face table
+                fb.flood_complex(cj.pts[:20000], 50, points_per_edge=cj.ppe)
+                barrier()
+                t0 = time.perf_counter()
+                dpts = cj.host_pts.to(dev, non_blocking=True)
+                r = fb.flood_complex(dpts, cj.n_lms, points_per_edge=cj.ppe)
+                barrier()
+                entry["e2e_wall_s"] = reduce_max(time.perf_counter() - t0)
+                entry["returned_simplices"] = len(r)
+                del dpts, r
+            configs[name] = entry
+            del cj
+
     if rank == 0:
-        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except OSError:
-            pass
-        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-        slots = SLOTS_PER_EVAL[dim]
-        peak_slots = sm_count * 128 * sm_max_mhz * 1e6
-        # dominant kernel: evaluations of the slowest rank's launch / its event time
-        per_launch_evals = E / world
-        kernel_rate = per_launch_evals / (eval_ms_t.item() * 1e-3)
+        slots, peak_slots = m["slots_per_eval"], m["peak_slots"]
         traffic = traffic_pruned = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
@@ -466,101 +562,85 @@ def run_cuda(args):
                 traffic_pruned = entry.get("pruned_dram_bytes_per_step")
         except OSError:
             pass
-        executed_frac = executed_t.item() / E
-        exh_kernel_rate = per_launch_evals / (exh_t[1].item() * 1e-3)
-        roofline_exhaustive = {
-            "kernel": "cover_eval_kernel<D, PRUNE=false> (every in-ball candidate evaluated; option prune=0)",
-            "achieved": exh_kernel_rate * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
-            "frac": exh_kernel_rate * slots / peak_slots, "traffic": traffic,
-            "kernel_ms_per_launch": exh_t[1].item(), "kernel_evals_per_s": exh_kernel_rate,
-            "value_evals_per_s": E / (exh_t[0].item() / args.steps * 1e-3),
-            "ms_per_step": exh_t[0].item() / args.steps,
-        }
+        executed_frac = dflt["executed_per_step"] / max(1.0, dflt["evals_per_step"])
         roofline = {
             "bound": "fp32-issue (CUDA-core FP32 lane slots; neither HBM nor tensor: contraction length is D=3)",
-            "kernel": "cover_eval_kernel<D, PRUNE=true>, seed pass + full pass (default product path)",
-            "achieved": kernel_rate * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
-            "frac": kernel_rate * slots / peak_slots,
-            "note": "achieved counts the ALGORITHMIC evaluations E (reference ball rule). The default sweep skips, "
-                    "exactly, candidates that cannot lower any minimum of a warp (SURVEY 8(f2)), so frac can "
-                    "exceed 1; executed_frac is the share of E actually evaluated, frac_executed the issue-slot "
-                    "utilisation of that executed work, roofline_exhaustive the same step without pruning.",
-            "executed_frac": executed_frac,
-            "frac_executed": kernel_rate * executed_frac * slots / peak_slots,
-            "traffic": traffic_pruned,
-            "slots_per_eval": slots, "evals_per_launch": per_launch_evals,
-            "kernel_ms_per_launch": eval_ms_t.item(), "kernel_evals_per_s": kernel_rate,
-            "peak_evals_per_s": peak_slots / slots,
+            "kernel": "cover_eval_kernel<D, PRUNE=false> (every in-ball candidate evaluated; option prune=0)",
+            "achieved": exh["kernel_evals_per_s"] * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
+            "frac": exh["kernel_frac"], "traffic": traffic,
+            "slots_per_eval": slots, "evals_per_launch": E / world, "kernel_ms_per_launch": exh["kernel_ms_per_launch"],
+            "kernel_evals_per_s": exh["kernel_evals_per_s"], "peak_evals_per_s": peak_slots / slots,
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
-            "flop_view": {"achieved_tflops": kernel_rate * (3 * dim - 1) / 1e12,
+            "flop_view": {"achieved_tflops": exh["kernel_evals_per_s"] * (3 * dim - 1) / 1e12,
                           "peak_tflops": 2 * peak_slots / 1e12},
-            "hbm_view": {"algorithmic_bytes_per_launch": 16.0 * n + 4.0 * (S_total / world) * R,
+            "hbm_view": {"algorithmic_bytes_per_launch": 16.0 * n + 4.0 * (job.S / world) * job.R,
                          "peak_gbs": peaks.get("hbm_gbs")},
+        }
+        default_path = {
+            "kernel": "cover_eval_kernel<D, PRUNE=true>, seed pass + full pass (what flood_complex runs by default)",
+            "ms_per_step": dflt["ms_per_step"], "evals_per_s": dflt["evals_per_s"],
+            "kernel_ms_per_launch": dflt["kernel_ms_per_launch"], "seed_ms_per_launch": dflt["seed_ms_per_launch"],
+            "executed_frac": executed_frac,
+            "frac_of_issue_peak_on_executed_work": dflt["kernel_evals_per_s"] * executed_frac * slots / peak_slots,
+            "algorithmic_speedup": exh["ms_per_step"] / dflt["ms_per_step"],
+            "traffic": traffic_pruned, "gpu_launches": dflt["launches"],
+            "note": "exact pruning (SURVEY 8(f2)): a warp skips candidates that are at least as far from the box of "
+                    "its sample brick as its largest running minimum; minima are bit-identical to the exhaustive "
+                    "sweep, executed_frac of the algorithmic evaluations E is performed",
         }
         fps_ms = fps_ms_total / max(1, fps_launches)
         fps_bytes = float(n) * (4 * dim + 8) * (n_lms - 1)      # N (4D + 8) per iteration
         fps_info = {
-            "kernel": "fps_kernel (register-resident)" if n <= 148 * 1024 * 8 else "fps_kernel (streaming)",
+            "kernel": "fps_kernel (register-resident)" if n <= 148 * 1024 * 8 else "fps_grid_kernel (bucketed)",
             "ms": fps_ms, "us_per_landmark": 1e3 * fps_ms / max(1, n_lms - 1),
             "bound": "hbm", "achieved": fps_bytes / (fps_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
             "unit": "GB/s (algorithmic bytes N(4D+8) per iteration)",
             "frac": (fps_bytes / (fps_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
             "note": "clouds up to 1.2M points stay in registers: no HBM traffic, the iteration is bound by the "
-                    "grid-wide argmax + sync (not by HBM); larger clouds stream from HBM or use the bucketed kernel",
+                    "grid-wide argmax + sync (not by HBM); larger clouds use the bucketed kernel",
         }
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": exh["evals_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": exh["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, {"simplices": S_total, "samples_per_simplex": int(R),
-                                         "evals_per_step": E, "returned_simplices": n_simplices}),
+            "config": config_dict(args.workload, world, {"simplices": job.S, "samples_per_simplex": int(job.R),
+                                                         "evals_per_step": E, "returned_simplices": n_simplices}),
+            "value_note": "every algorithmic evaluation executed (library option prune=0): the step the roofline "
+                          "describes. flood_complex's default path prunes exactly and is faster: see default_path "
+                          "(value_default_path = E / its step time) and e2e",
+            "value_default_path": dflt["evals_per_s"],
             "e2e": {"value": E / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * dim * 4 * world),
-                    "d2h_bytes_per_step": int((S_total * (2 ** K - 1) * 4 + host_lms_bytes) * world),
+                    "d2h_bytes_per_step": int((job.S * (2 ** job.K - 1) * 4 + n_lms * dim * 4) * world),
                     "flood_complex_wall_s": e2e_s, "steps": e2e_steps,
+                    "path": "public API, default (exactly pruned) sweep",
+                    "exhaustive": {"value": E / e2e_exh_s, "flood_complex_wall_s": e2e_exh_s},
+                    "single_gpu_wall_s": e2e_single_s,
+                    "scaling_efficiency": e2e_single_s / (world * e2e_s),
                     "stage_seconds_serialised": stage_seconds,
                     "includes": "H2D of the cloud, landmark FPS, host Delaunay, kernels, D2H, complex assembly"},
-            "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps * world,
-            "value_note": "E / step time of the default product path, whose sweep is pruned EXACTLY (bit-identical "
-                          "minima; executed_frac of E is evaluated, SURVEY 8(f2)); value_exhaustive is the same step "
-                          "with every evaluation executed (option prune=0), the kernel roofline_exhaustive describes",
-            "value_exhaustive": roofline_exhaustive["value_evals_per_s"],
+            "gpu_launches": exh["launches"],
             "roofline": roofline,
-            "roofline_exhaustive": roofline_exhaustive,
+            "default_path": default_path,
             "roofline_fps": fps_info,
             "clocks": clock_info,
             "timed_region_wall_s": wall_s,
         }
+        if configs:
+            line["configs"] = configs
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = reference_triton(args.workload)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, host_pts.numpy(), lms.cpu().numpy(), cells,
-                                                weights.cpu().numpy())
+            arm = cpu_arm(args.workload, args.cpu_sample_simplices, 1, 0)
+            line["cpu_baseline"] = {k: arm[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores",
+                                                        "value_single_thread", "note", "one_off_seconds",
+                                                        "projected_full_job_s")}
+            if not args.no_ref_config1:
+                line["cpu_baseline"]["reference_config1"] = reference_config1()
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(args, pts, lms, cells, weights):
-    """Oracle port of the reference CPU path on a bounded sample of this job (rank 0, N = 1)."""
-    from scipy.spatial import KDTree
-
-    from oracle import flood_oracle, native
-
-    dim = pts.shape[1]
-    rng = np.random.default_rng(0)
-    sel = rng.permutation(len(cells))[: args.cpu_sample_simplices]
-    verts = lms[cells[sel]]
-    centers, radii = flood_oracle.bounding_balls(verts, dim)
-    counts = native.ball_counts(pts, centers, radii)
-    t0 = time.perf_counter()
-    tree = KDTree(pts)
-    build_s = time.perf_counter() - t0
-    dt, evals, _ = cpu_reference_sample(pts, verts, weights, counts, tree=tree, workers=1)
-    return {"value": evals / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{len(sel)} of {len(cells)} simplices (random, seeded), {weights.shape[0]} samples each; "
-                      f"scipy KDTree.query single-threaded as in the reference ({dt:.1f} s) over a tree of the "
-                      f"full cloud (build {build_s:.1f} s, not included)",
-            "host_cores": os.cpu_count(),
-            "projected_full_job_s": build_s + dt * len(cells) / len(sel)}
 
 
 def main():
@@ -571,14 +651,19 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference", "reference_triton"])
     ap.add_argument("--workload", default="torus_1m_1k", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-simplices", type=int, default=200)
-    ap.add_argument("--ref-simplices-per-step", type=int, default=40)
+    ap.add_argument("--config-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-simplices", type=int, default=400)
+    ap.add_argument("--ref-simplices-per-step", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-ref-config1", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference_triton":
-        run_reference_triton(args)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference_triton", **reference_triton(args.workload)}), flush=True)
     else:
         run_cuda(args)
 

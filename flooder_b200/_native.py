@@ -76,6 +76,8 @@ def cdll() -> ctypes.CDLL:
         lib.flood_covering_plan_f32.argtypes = [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]
         lib.flood_face_max_f32.argtypes = [c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]
         lib.flood_set_option.argtypes = [ctypes.c_char_p, c_int]
+        lib.flood_launch_count.argtypes = [c_int]
+        lib.flood_launch_count.restype = ctypes.c_longlong
         for fn in ("flood_device_info", "flood_fps_f32", "flood_fps_grid_f32", "flood_cloud_build_f32", "flood_bounding_balls_f32",
                    "flood_covering_radius_f32", "flood_covering_plan_f32", "flood_covering_bricks", "flood_face_max_f32",
                    "flood_set_option"):
@@ -86,6 +88,7 @@ def cdll() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "flood_abi_version", "flood_last_error", "flood_device_info", "flood_set_option", "flood_kernel_ms",
+    "flood_launch_count",
     "flood_fps_workspace_bytes", "flood_fps_f32", "flood_fps_grid_f32",
     "flood_cloud_workspace_bytes", "flood_cloud_build_f32",
     "flood_bounding_balls_f32",

@@ -258,11 +258,15 @@ def covering_values(
     grid_mode: bool,
     samples: Optional[torch.Tensor] = None,
     return_details: bool = False,
+    stats: Optional[dict] = None,
 ):
     """Device part of one dimension pass: bounding balls -> covering-radius kernel -> face maxima.
 
     Returns a float32 tensor ``(S, 2^K - 1)`` (grid mode; column ``m-1`` belongs to the face whose
-    vertex positions are the set bits of ``m``) or ``(S, 1)`` (random mode).
+    vertex positions are the set bits of ``m``) or ``(S, 1)`` (random mode).  ``stats``, when
+    given, receives the device-side work counters of the call (``evals`` = algorithmic count E,
+    ``executed`` = evaluations actually performed; summed over slabs) without changing what is
+    enqueued.
     """
     ext = _native.ext()
     verts = simplex_vertices.to(torch.float32).contiguous()
@@ -286,16 +290,21 @@ def covering_values(
         min_d2, counts, evals, executed = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts, w, samples,
                                                               centers, radii)
         values = ext.face_max(min_d2, support, K)
+        if stats is not None:
+            stats["evals"], stats["executed"] = evals, executed
     else:
         # memory-bounded: the simplices go through the kernel in slabs, only the face values stay
         parts = []
         for lo in range(0, S, rows):
             hi = min(S, lo + rows)
-            min_d2, _c, _e, _x = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts[lo:hi], w,
-                                                     None if samples is None else samples[lo:hi].contiguous(),
-                                                     centers[lo:hi], radii[lo:hi])
+            min_d2, _c, evals, executed = ext.covering_radius(cloud.workspace, cloud.n, cloud.d, verts[lo:hi], w,
+                                                              None if samples is None else samples[lo:hi].contiguous(),
+                                                              centers[lo:hi], radii[lo:hi])
             parts.append(ext.face_max(min_d2, support, K))
             del min_d2
+            if stats is not None:
+                stats["evals"] = evals if lo == 0 else stats["evals"] + evals
+                stats["executed"] = executed if lo == 0 else stats["executed"] + executed
         values = torch.cat(parts, dim=0)
     if order is not None:
         values = torch.empty_like(values).index_copy_(0, order, values)
@@ -312,6 +321,21 @@ def covering_cost(cloud: PreparedCloud, simplex_vertices: torch.Tensor) -> torch
     ext = _native.ext()
     centers, radii = ext.bounding_balls(simplex_vertices.to(torch.float32).contiguous())
     return ext.covering_plan(cloud.workspace, cloud.n, cloud.d, centers, radii).to(torch.float32)
+
+
+def device_pass(cloud: PreparedCloud, simplex_vertices: torch.Tensor, weights: torch.Tensor, grid_mode: bool,
+                shard: Optional["fdist.Shard"] = None, stats: Optional[dict] = None) -> torch.Tensor:
+    """Everything ``flood_complex`` enqueues on the device for one dimension pass, given the
+    prepared cloud: [cost plan + partition over ranks] -> bounding balls -> covering-radius kernel
+    -> face maxima -> [all-gather of the per-simplex values].  Asynchronous; returns the device
+    tensor of values for all simplices.  ``bench.py`` times exactly this function (plus the cloud
+    build), so the benchmarked path cannot drift from the product path."""
+    if shard is None:
+        return covering_values(cloud, simplex_vertices, weights, grid_mode=grid_mode, stats=stats)
+    return fdist.sharded_covering_values(
+        shard, simplex_vertices,
+        lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode, stats=stats),
+        cost=covering_cost(cloud, simplex_vertices))
 
 
 def _scatter_face_values(table: FaceTable, cell_values: np.ndarray, values: Dict[int, np.ndarray]) -> None:
@@ -409,11 +433,7 @@ def flood_complex(
     def launch(d_simplices_np: np.ndarray, weights: torch.Tensor) -> torch.Tensor:
         """Enqueue one dimension pass (asynchronous); returns the device tensor of values."""
         simplex_vertices = lms32[torch.as_tensor(d_simplices_np, device=device)]
-        if shard is None:
-            return covering_values(cloud, simplex_vertices, weights, grid_mode=grid_mode)
-        return fdist.sharded_covering_values(
-            shard, simplex_vertices, lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode),
-            cost=covering_cost(cloud, simplex_vertices))
+        return device_pass(cloud, simplex_vertices, weights, grid_mode, shard)
 
     # Grid mode on full-dimensional cells needs nothing but the cells: enqueue the kernels first
     # and build the face table on the host while the GPU works.

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -62,6 +63,9 @@ void kernel_timer_stop(const char *name, cudaStream_t st) {
     t.pending = true;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 int device_sm_count() {
     static thread_local int cached_dev = -1, cached_sms = 0;
     int dev = 0;
@@ -118,6 +122,10 @@ int flood_kernel_ms(const char *name, double *total_ms, long *launches, int rese
     if (launches) *launches = it->second.launches;
     if (reset) { it->second.total_ms = 0.0; it->second.launches = 0; }
     return FLOOD_OK;
+}
+
+long long flood_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 size_t flood_fps_workspace_bytes(int64_t n, int d, int64_t n_lms) { return fps_workspace_bytes(n, d, n_lms); }

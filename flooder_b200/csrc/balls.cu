@@ -97,6 +97,7 @@ int bounding_balls(const float *verts, int64_t S, int K, int d, float *centers, 
     const int threads = 128;
     bounding_balls_kernel<<<(unsigned)((S + threads - 1) / threads), threads, 0, st>>>(verts, S, K, d,
                                                                                       centers, radii);
+    count_launches(1);
     FLOOD_LAUNCH_CHECK("bounding_balls_kernel");
     return FLOOD_OK;
 }
@@ -110,6 +111,7 @@ int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *suppor
     if (S > 2147483647LL) return set_error(FLOOD_E_UNSUPPORTED, "face_max: S too large");
     const size_t smem = sizeof(unsigned) * (support ? (size_t(1) << K) : 1);
     face_max_kernel<<<(unsigned)S, 256, smem, st>>>(min_dist2, R, support, K, out);
+    count_launches(1);
     FLOOD_LAUNCH_CHECK("face_max_kernel");
     return FLOOD_OK;
 }

@@ -208,6 +208,7 @@ int cloud_build(const float *pts, int64_t n, int d, int points_per_cell, void *w
     if (pd == 2) scatter_kernel<2><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
     else if (pd == 4) scatter_kernel<4><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
     else scatter_kernel<8><<<blocks, threads, 0, st>>>(pts, n, d, cell_id, cell_start, cell_fill, perm, out);
+    count_launches(6);
     FLOOD_LAUNCH_CHECK("cloud_build kernels");
     return FLOOD_OK;
 }

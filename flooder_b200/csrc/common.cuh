@@ -39,6 +39,8 @@ int get_option(const char *name, int fallback);
 void kernel_timer_start(const char *name, cudaStream_t st);
 void kernel_timer_stop(const char *name, cudaStream_t st);
 int device_sm_count();
+// every kernel the library launches is counted (flood_launch_count; bench.py's gpu_launches)
+void count_launches(int n);
 
 // --------------------------------------------------------------------------------------
 // prepared cloud: layout of the workspace filled by flood_cloud_build_f32
@@ -150,6 +152,26 @@ template <int D> __device__ __forceinline__ typename Rec<D>::type rec_ldg(const 
         r.b = __ldg(&p->b);
         return r;
     }
+}
+
+// asynchronous global -> shared copy of one record (cp.async, LDGSTS in SASS): no register staging,
+// completion is awaited per thread with cp_async_wait<N>() (N = groups still allowed in flight)
+template <int D> __device__ __forceinline__ void rec_cp_async(typename Rec<D>::type *smem_dst,
+                                                              const typename Rec<D>::type *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if constexpr (sizeof(typename Rec<D>::type) == 8) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src));
+    } else if constexpr (sizeof(typename Rec<D>::type) == 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src));
+    } else {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16),
+                     "l"(reinterpret_cast<const char *>(gmem_src) + 16));
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 // --------------------------------------------------------------------------------------

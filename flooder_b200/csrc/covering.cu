@@ -152,6 +152,7 @@ int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, 
     const int threads = 128;
     const long long blocks = (S * 32 + threads - 1) / threads;
     cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
+    count_launches(1);
     FLOOD_LAUNCH_CHECK("cover_plan_kernel");
     return FLOOD_OK;
 }
@@ -256,6 +257,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
         cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
         cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base, S);
         if (P.item_base_seed) cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base_seed, S);
+        count_launches(P.item_base_seed ? 4 : 3);   // fill, plan, scan (+ scan)
     }
     FLOOD_LAUNCH_CHECK("cover plan kernels");
     switch (d) {

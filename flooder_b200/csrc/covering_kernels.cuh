@@ -8,6 +8,7 @@ namespace flood {
 
 
 constexpr int kUnroll = 4;       // candidates per inner-loop trip
+constexpr int kAsyncLPL = 2;       // cp.async gather: records per lane and staging buffer
 constexpr int kBoundRefresh = 16;  // pruned sweep: candidates swept between refreshes of the warp bound
 
 struct CoverParams {
@@ -26,6 +27,7 @@ struct CoverParams {
     long long *item_base;    // [S+1]   exclusive prefix of chunks per simplex
     long long *item_base_seed;  // [S+1] the same for the seed pass (longer chunks), or null
     int chunk_seed;          // target tested points per chunk of the seed pass
+    int async_gather;        // 1: records are staged through shared memory with cp.async (double-buffered)
     unsigned long long *queue;
     unsigned long long *executed;   // evaluations actually performed (pruned sweeps skip some)
     int stream_stride;       // 1 = every stream position; k > 1 = every k-th (seed pass of the pruned mode)
@@ -347,13 +349,18 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     constexpr int kMaxT = MAXT;
     constexpr int LPL = D <= 4 ? 4 : 2;  // records in flight per lane while gathering
     constexpr int UNIT = 32 * LPL;       // stream positions per warp work unit
+    constexpr int ALPL = kAsyncLPL;      // the same for the cp.async path (staged in shared memory)
+    constexpr int AUNIT = 32 * ALPL;
     using RecT = typename Rec<D>::type;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
     const int tile_cap = P.tile_cap;
     RecT *tile = reinterpret_cast<RecT *>(smem_raw);
-    int *run_start = reinterpret_cast<int *>(smem_raw + (size_t)(tile_cap + kUnroll) * sizeof(RecT));
+    // per-warp staging ring of the cp.async gather: 2 buffers x AUNIT records
+    RecT *stage = tile + (tile_cap + kUnroll) + (size_t)(threadIdx.x >> 5) * (P.async_gather ? 2 * AUNIT : 0);
+    int *run_start = reinterpret_cast<int *>(smem_raw + (size_t)(tile_cap + kUnroll) * sizeof(RecT) +
+                                             (P.async_gather ? (size_t)(NT >> 5) * 2 * AUNIT * sizeof(RecT) : 0));
     int *run_pos = run_start + NT;
     __shared__ int warp_sums[32];
     __shared__ int s_fill;
@@ -429,28 +436,37 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             // pruned mode starts from what other chunks / the seed pass already found (an upper
             // bound of the minimum); unused slots carry 0 so that they never loosen the warp bound
             m[t] = PRUNE ? 0.f : INFINITY;
-            if (t < nt && r < P.R) {
-                if (PRUNE) m[t] = __ldcg(P.out + s * P.R + r);
-                if (P.samples) {
+            if (PRUNE && t < nt && r < P.R) m[t] = __ldcg(P.out + s * P.R + r);
+#pragma unroll
+            for (int a = 0; a < D; ++a) x[t][a] = c[a];
+        }
+        if (P.samples) {
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                const long long r = (long long)(g0 + t) * 32 + lane;
+                if (t < nt && r < P.R) {
 #pragma unroll
                     for (int a = 0; a < D; ++a) x[t][a] = __ldg(P.samples + (s * P.R + r) * D + a);
-                } else {
-                    // x = sum_k w[r,k] * v[s,k,:], FMA chain over k ascending (== the reference's
-                    // float32 matmul, core.py:188)
-                    const float *w = P.weights + r * P.K;
-                    const float *v = P.verts + s * P.K * D;
-                    const float w0 = __ldg(w);
+                }
+            }
+        } else {
+            // x = sum_k w[r,k] * v[s,k,:], FMA chain over k ascending (== the reference's float32
+            // matmul, core.py:188); k is the outer loop so that a vertex is loaded once per warp
+#pragma unroll 1
+            for (int k = 0; k < P.K; ++k) {
+                float v[D];
 #pragma unroll
-                    for (int a = 0; a < D; ++a) x[t][a] = __fmul_rn(w0, __ldg(v + a));
-                    for (int k = 1; k < P.K; ++k) {
-                        const float wk = __ldg(w + k);
+                for (int a = 0; a < D; ++a) v[a] = __ldg(P.verts + (s * P.K + k) * D + a);
 #pragma unroll
-                        for (int a = 0; a < D; ++a) x[t][a] = fmaf(wk, __ldg(v + k * D + a), x[t][a]);
+                for (int t = 0; t < kMaxT; ++t) {
+                    const long long r = (long long)(g0 + t) * 32 + lane;
+                    if (t < nt && r < P.R) {
+                        const float wk = __ldg(P.weights + r * P.K + k);
+#pragma unroll
+                        for (int a = 0; a < D; ++a)
+                            x[t][a] = k == 0 ? __fmul_rn(wk, v[a]) : fmaf(wk, v[a], x[t][a]);
                     }
                 }
-            } else {
-#pragma unroll
-                for (int a = 0; a < D; ++a) x[t][a] = c[a];
             }
         }
 
@@ -539,40 +555,141 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
             __syncthreads();
         };
 
+        // ball test (+ CTA-level cull) of up to N records per lane, warp-ballot compaction into the tile
+        unsigned inball = 0;   // records inside the ball seen by this warp (lane-uniform)
+        auto test_and_compact = [&](auto &rec, int nrec) __attribute__((always_inline)) {
+            constexpr int N = sizeof(rec) / sizeof(rec[0]);
+            unsigned keep[N];
+            int nkeep = 0;
+#pragma unroll
+            for (int v = 0; v < N; ++v) {
+                bool pass = false, near = false;
+                if (lane + 32 * v < nrec) {
+                    float q[D];
+                    rec_unpack<D>(rec[v], q);
+                    // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
+                    float t = q[0] - c[0];
+                    float acc = t * t;
+#pragma unroll
+                    for (int a2 = 1; a2 < D; ++a2) {
+                        t = q[a2] - c[a2];
+                        acc = fmaf(t, t, acc);
+                    }
+                    pass = acc <= r2;
+                    if (PRUNE && pass) {
+                        // CTA-level cull: a record at least sqrt(U) away from the box of the CTA's
+                        // samples cannot lower any of their minima
+                        float box2 = 0.f;
+#pragma unroll
+                        for (int a2 = 0; a2 < D; ++a2) {
+                            const float e2 = fmaxf(fmaxf(s_cbox[a2] - q[a2], q[a2] - s_cbox[D + a2]), 0.f);
+                            box2 = fmaf(e2, e2, box2);
+                        }
+                        near = box2 * 0.9999f <= U;
+                    }
+                }
+                const unsigned bm = __ballot_sync(0xffffffffu, pass);
+                inball += (unsigned)__popc(bm);
+                keep[v] = PRUNE ? __ballot_sync(0xffffffffu, near) : bm;
+                nkeep += __popc(keep[v]);
+            }
+            int wbase = 0;
+            if (lane == 0 && nkeep) wbase = atomicAdd(&s_fill, nkeep);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+            for (int v = 0; v < N; ++v) {
+                if ((keep[v] >> lane) & 1u) tile[wbase + __popc(keep[v] & lt_mask)] = rec[v];
+                wbase += __popc(keep[v]);
+            }
+        };
+
         // ---- stream the candidate window -----------------------------------------------------
         // Rows of the ball -> runs of the cell-sorted cloud, NT rows at a time; the runs of a
         // batch (clipped to this item's window of the stream) are gathered by the warps in units
         // of UNIT consecutive stream positions: coalesced record loads, ball test, warp-ballot
         // compaction into the tile.  The tile is swept whenever the next round might overflow it.
         int fill = 0;
-        unsigned inball = 0;   // records inside the ball seen by this warp (lane-uniform)
-        int carry = 0;         // stream offset of the current row batch
-        for (int rb = 0; rb < bc.nrows; rb += NT) {
-            if (carry >= win_hi) break;
-            const int row = rb + tid;
-            int a = 0, len = 0;
-            if (row < bc.nrows) row_run(bc, row, gp, P.cell_start, a, len);
-            int batch_total;
-            const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
-            carry += batch_total;
-            if (carry <= win_lo) continue;
-            // clip the run to this chunk's window of the stream; a seed pass (stride > 1) takes
-            // every stride-th record of each clipped run
-            const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
-            const int len2 = max(0, s1 - s0);
-            int total2;
-            const int pos2 = block_exclusive_scan((len2 + stride - 1) / stride, warp_sums, total2);
-            run_start[tid] = a + (s0 - off);
-            run_pos[tid] = pos2;
-            if (tid == 0) run_pos[NT] = total2;
-            __syncthreads();
-
-            for (int q0 = 0; q0 < total2;) {
-                if (fill > 0 && tile_cap - fill < min(total2 - q0, UNIT * W)) {
-                    sweep(fill);
-                    fill = 0;
+        int carry = 0;         // stream offset of the next row batch
+        int rb = 0;            // first row of the next row batch
+        int q0 = 0, total2 = 0;  // progress inside the current row batch (stream positions)
+        bool stream_done = false;
+        // One sweep call site (the sweep is instantiated for every group count): alternate between
+        // "gather until the tile cannot take the next round" and "sweep".
+        for (;;) {
+            while (!stream_done) {
+                if (q0 >= total2) {
+                    // next batch of NT rows -> runs
+                    if (rb >= bc.nrows || carry >= win_hi) {
+                        stream_done = true;
+                        break;
+                    }
+                    const int row = rb + tid;
+                    rb += NT;
+                    int a = 0, len = 0;
+                    if (row < bc.nrows) row_run(bc, row, gp, P.cell_start, a, len);
+                    int batch_total;
+                    const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
+                    carry += batch_total;
+                    q0 = total2 = 0;
+                    if (carry <= win_lo) continue;
+                    // clip the run to this chunk's window of the stream; a seed pass (stride > 1)
+                    // takes every stride-th record of each clipped run
+                    const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
+                    const int len2 = max(0, s1 - s0);
+                    const int pos2 = block_exclusive_scan((len2 + stride - 1) / stride, warp_sums, total2);
+                    run_start[tid] = a + (s0 - off);
+                    run_pos[tid] = pos2;
+                    if (tid == 0) run_pos[NT] = total2;
+                    __syncthreads();
+                    continue;
                 }
-                const int take = min(total2 - q0, tile_cap - fill);
+                if (fill > 0 && tile_cap - fill < min(total2 - q0, UNIT * W)) break;   // tile full: sweep first
+            const int take = min(total2 - q0, tile_cap - fill);
+            if (P.async_gather) {
+                // cp.async (LDGSTS) double buffering: the records of the warp's next unit are in
+                // flight to its staging buffer while the current unit is tested and compacted
+                const int nunits = (take + AUNIT - 1) / AUNIT;
+                auto issue = [&](int unit, int buf) {
+                    int p = q0 + unit * AUNIT;
+                    const int p1 = min(p + AUNIT, q0 + take);
+                    const int n_u = p1 - p;
+                    int i = find_run(run_pos, NT, p, lane);
+                    RecT *dst = stage + buf * AUNIT;
+                    while (p < p1) {
+                        const int e = run_pos[i + 1];
+                        if (e <= p) { ++i; continue; }
+                        const int nrec = min(e, p1) - p;
+                        const RecT *src = points + run_start[i] + (long long)(p - run_pos[i]) * stride;
+                        for (int k = lane; k < nrec; k += 32) rec_cp_async<D>(dst + k, src + (long long)k * stride);
+                        dst += nrec;
+                        p += nrec;
+                    }
+                    cp_async_commit();
+                    return n_u;
+                };
+                int unit = warp, buf = 0, n_cur = 0;
+                if (unit < nunits) n_cur = issue(unit, 0);
+                while (unit < nunits) {
+                    const int next = unit + W;
+                    int n_next = 0;
+                    if (next < nunits) {
+                        n_next = issue(next, buf ^ 1);
+                        cp_async_wait<1>();
+                    } else {
+                        cp_async_wait<0>();
+                    }
+                    __syncwarp();
+                    RecT rec[ALPL];
+#pragma unroll
+                    for (int v = 0; v < ALPL; ++v)
+                        if (lane + 32 * v < n_cur) rec[v] = stage[buf * AUNIT + lane + 32 * v];
+                    test_and_compact(rec, n_cur);
+                    __syncwarp();   // every lane has read the buffer before it is refilled
+                    unit = next;
+                    buf ^= 1;
+                    n_cur = n_next;
+                }
+            } else {
                 const int nunits = (take + UNIT - 1) / UNIT;
                 for (int unit = warp; unit < nunits; unit += W) {
                     int p = q0 + unit * UNIT;
@@ -589,57 +706,21 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             const int k = lane + 32 * v;
                             if (k < nrec) rec[v] = rec_ldg<D>(src + (long long)k * stride);
                         }
-                        unsigned keep[LPL];
-                        int nkeep = 0;
-#pragma unroll
-                        for (int v = 0; v < LPL; ++v) {
-                            bool pass = false, near = false;
-                            if (lane + 32 * v < nrec) {
-                                float q[D];
-                                rec_unpack<D>(rec[v], q);
-                                // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
-                                float t = q[0] - c[0];
-                                float acc = t * t;
-#pragma unroll
-                                for (int a2 = 1; a2 < D; ++a2) {
-                                    t = q[a2] - c[a2];
-                                    acc = fmaf(t, t, acc);
-                                }
-                                pass = acc <= r2;
-                                if (PRUNE && pass) {
-                                    // CTA-level cull: a record at least sqrt(U) away from the box of the
-                                    // CTA's samples cannot lower any of their minima
-                                    float box2 = 0.f;
-#pragma unroll
-                                    for (int a2 = 0; a2 < D; ++a2) {
-                                        const float e2 = fmaxf(fmaxf(s_cbox[a2] - q[a2], q[a2] - s_cbox[D + a2]), 0.f);
-                                        box2 = fmaf(e2, e2, box2);
-                                    }
-                                    near = box2 * 0.9999f <= U;
-                                }
-                            }
-                            const unsigned bm = __ballot_sync(0xffffffffu, pass);
-                            inball += (unsigned)__popc(bm);
-                            keep[v] = PRUNE ? __ballot_sync(0xffffffffu, near) : bm;
-                            nkeep += __popc(keep[v]);
-                        }
-                        int wbase = 0;
-                        if (lane == 0 && nkeep) wbase = atomicAdd(&s_fill, nkeep);
-                        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-                        for (int v = 0; v < LPL; ++v) {
-                            if ((keep[v] >> lane) & 1u) tile[wbase + __popc(keep[v] & lt_mask)] = rec[v];
-                            wbase += __popc(keep[v]);
-                        }
+                        test_and_compact(rec, nrec);
                         p += nrec;
                     }
                 }
+            }
                 __syncthreads();
                 fill = s_fill;
                 q0 += take;
             }
+            if (fill > 0) {
+                sweep(fill);
+                fill = 0;
+            }
+            if (stream_done) break;
         }
-        if (fill > 0) sweep(fill);
 
         // ---- merge -----------------------------------------------------------------------------
 #pragma unroll
@@ -670,10 +751,12 @@ int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
     const int NT = sh.W * 32;
     // tile capacity: what the shared memory of an SM allows for MINB resident CTAs (narrow CTAs
     // of small sample sets pack more per SM and get proportionally smaller tiles)
-    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int) + 2048;
+    P.async_gather = get_option("async_gather", 1) != 0;
+    const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * kAsyncLPL * sizeof(RecT) : 0;
+    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int) + staging + 2048;
     int per_sm_target = (MAXW * MINB * 32) / NT;
     if (per_sm_target < 1) per_sm_target = 1;
-    if (per_sm_target > 8) per_sm_target = 8;
+    if (per_sm_target > 20) per_sm_target = 20;
     long long cap = ((long long)(227 * 1024) / per_sm_target - (long long)fixed) / (long long)sizeof(RecT);
     if (cap > 4096) cap = 4096;
     const int forced_cap = get_option("tile_cap", 0);
@@ -681,7 +764,7 @@ int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
     if (cap < 2 * NT) cap = 2 * NT;
     cap = cap / kUnroll * kUnroll;
     P.tile_cap = (int)cap;
-    const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int);
+    const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + staging + (size_t)(2 * NT + 1) * sizeof(int);
     FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FLOOD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -702,6 +785,7 @@ int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
         if (P.item_base_seed) P.item_base = P.item_base_seed;   // chunks seed_stride times longer
         if (timed) kernel_timer_start("cover_seed", st);
         kern<<<grid, NT, smem, st>>>(P);
+        count_launches(1);
         if (timed) kernel_timer_stop("cover_seed", st);
         P.item_base = main_base;
         P.queue = queue0 + 1;
@@ -709,6 +793,7 @@ int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
     P.stream_stride = 1;
     P.count_work = 1;
     kern<<<grid, NT, smem, st>>>(P);
+    count_launches(1);
     P.queue = queue0;
     if (timed) kernel_timer_stop("cover_eval", st);
     FLOOD_LAUNCH_CHECK("cover_eval_kernel");

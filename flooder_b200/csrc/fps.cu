@@ -293,6 +293,7 @@ int launch_fps(FpsParams &P, cudaStream_t st, bool probe_only, long long *capaci
     const bool timed = get_option("time_kernels", 0) != 0;
     if (timed) kernel_timer_start("fps", st);
     FLOOD_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(threads), args, 0, st));
+    count_launches(1);
     if (timed) kernel_timer_stop("fps", st);
     return FLOOD_OK;
 }
@@ -332,6 +333,7 @@ int launch_fps_grid(FpsGridParams &G, long long ncells_bound, cudaStream_t st, b
     const bool timed = get_option("time_kernels", 0) != 0;
     if (timed) kernel_timer_start("fps", st);
     FLOOD_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(threads), args, 0, st));
+    count_launches(1);
     if (timed) kernel_timer_stop("fps", st);
     *launched = true;
     return FLOOD_OK;

@@ -197,5 +197,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("covering_plan", &covering_plan);
     m.def("covering_bricks", &covering_bricks);
     m.def("set_option", &set_option);
+    m.def("launch_count", [](bool reset) { return (int64_t)flood_launch_count(reset ? 1 : 0); });
     m.def("kernel_ms", &kernel_ms);
 }

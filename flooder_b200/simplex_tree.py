@@ -169,7 +169,9 @@ class SimplexTree(PersistenceMixin):
     def from_arrays(cls, faces: Dict[int, np.ndarray], values: Dict[int, np.ndarray]) -> "SimplexTree":
         st = cls()
         for k in sorted(faces):
-            st._f.update(zip(map(tuple, faces[k].tolist()), values[k].tolist()))
+            # zip over the columns builds the key tuples directly (no intermediate row lists)
+            cols = [faces[k][:, j].tolist() for j in range(faces[k].shape[1])]
+            st._f.update(zip(zip(*cols), values[k].tolist()))
         return st
 
     def insert(self, simplex: Iterable[int], filtration: float = 0.0) -> bool:

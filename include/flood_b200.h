@@ -154,6 +154,10 @@ int flood_set_option(const char *name, int value);
  * ("cover_eval", "fps") and reports the accumulated device time and launch count. */
 int flood_kernel_ms(const char *name, double *total_ms, long *launches, int reset);
 
+/* Number of kernels the library has launched in this process (every launch site counts itself);
+ * reset != 0 returns the count and clears it.  bench.py reports it as gpu_launches. */
+long long flood_launch_count(int reset);
+
 #ifdef __cplusplus
 }
 #endif
