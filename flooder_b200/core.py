@@ -88,9 +88,12 @@ def generate_grid(n: int, dim: int, device, dtype=torch.float32):
             verts_k.append(torch.as_tensor(axes[~np.isin(axes, zero_set)], device=device))
         face_idxs.append(torch.stack(rows_k))
         vertex_idxs.append(torch.stack(verts_k))
-    weights = torch.empty((counts.shape[0], dim + 1), dtype=dtype, device=device)
-    torch.divide(torch.as_tensor(counts, device=device), n - 1, out=weights)
-    return weights, vertex_idxs, face_idxs
+    # divided on the CPU and then moved: on a CUDA device torch.divide by a scalar multiplies by the
+    # rounded reciprocal (one ulp off for some k); the CPU quotient is what the reference's CPU path
+    # sees (see _grid_weights_cached)
+    weights = torch.empty((counts.shape[0], dim + 1), dtype=dtype)
+    torch.divide(torch.as_tensor(counts), n - 1, out=weights)
+    return weights.to(device), vertex_idxs, face_idxs
 
 
 def generate_uniform_weights(num_rand: int, dim: int, device, dtype=torch.float32) -> torch.Tensor:
@@ -105,9 +108,15 @@ def generate_uniform_weights(num_rand: int, dim: int, device, dtype=torch.float3
 
 @functools.lru_cache(maxsize=16)
 def _grid_weights_cached(n: int, dim: int, device_str: str) -> torch.Tensor:
-    counts = torch.as_tensor(_lattice(n, dim), device=device_str)
-    weights = torch.empty(counts.shape, dtype=torch.float32, device=device_str)
+    # The quotients k / (n - 1) are formed on the CPU (correctly rounded float32 division, what the
+    # reference's CPU path uses) and then copied: on a CUDA device torch.divide by a
+    # Python scalar multiplies by the rounded reciprocal, which is off by one ulp for some k -- one
+    # ulp of a weight moves a sample point by up to one ulp of its coordinates, visible against the
+    # exact KD-tree distances at 1 M points.
+    counts = torch.as_tensor(_lattice(n, dim))
+    weights = torch.empty(counts.shape, dtype=torch.float32)
     torch.divide(counts, n - 1, out=weights)
+    weights = weights.to(device_str)
     weights._flood_cached = True
     return weights
 

@@ -17,16 +17,19 @@ __device__ __forceinline__ float from_ordered_bits(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+constexpr int GA = kMaxGridAxes;
+
 __global__ void bbox_init_kernel(unsigned *bbox) {
     int t = threadIdx.x;
-    if (t < 3) bbox[t] = 0xffffffffu;      // running minima
-    else if (t < 6) bbox[t] = 0u;          // running maxima
+    if (t < GA) bbox[t] = 0xffffffffu;          // running minima
+    else if (t < 2 * GA) bbox[t] = 0u;          // running maxima
 }
 
-// bounding box over the first min(d,3) coordinates
+// bounding box over the binned coordinates
 __global__ void bbox_kernel(const float *__restrict__ pts, int64_t n, int d, unsigned *bbox) {
-    const int g = d < 3 ? d : 3;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int g = grid_axes(d);
+    float lo[GA], hi[GA];
+    for (int a = 0; a < GA; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         for (int a = 0; a < g; ++a) {
@@ -42,7 +45,7 @@ __global__ void bbox_kernel(const float *__restrict__ pts, int64_t n, int d, uns
         }
         if ((threadIdx.x & 31) == 0 && lo[a] <= hi[a]) {
             atomicMin(&bbox[a], ordered_bits(lo[a]));
-            atomicMax(&bbox[3 + a], ordered_bits(hi[a]));
+            atomicMax(&bbox[GA + a], ordered_bits(hi[a]));
         }
     }
 }
@@ -50,20 +53,22 @@ __global__ void bbox_kernel(const float *__restrict__ pts, int64_t n, int d, uns
 // Choose a cubic cell edge h so that the box holds ~ n / points_per_cell cells.
 __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int points_per_cell,
                                    int64_t max_cells, GridParams *gp) {
-    const int g = d < 3 ? d : 3;
-    float lo[3] = {0.f, 0.f, 0.f}, ext[3] = {0.f, 0.f, 0.f};
+    const int g = grid_axes(d);
+    float lo[GA], ext[GA];
     double vol = 1.0;
     int live = 0;
+    for (int a = 0; a < GA; ++a) { lo[a] = 0.f; ext[a] = 0.f; }
     for (int a = 0; a < g; ++a) {
         lo[a] = from_ordered_bits(bbox[a]);
-        ext[a] = from_ordered_bits(bbox[3 + a]) - lo[a];
+        ext[a] = from_ordered_bits(bbox[GA + a]) - lo[a];
         if (ext[a] > 0.f) { vol *= (double)ext[a]; ++live; }
     }
     double target = (double)n / (double)(points_per_cell > 0 ? points_per_cell : 32);
     if (target < 1.0) target = 1.0;
     if (target > (double)max_cells) target = (double)max_cells;
     float h = 1.0f;
-    int nc[3] = {1, 1, 1};
+    int nc[GA];
+    for (int a = 0; a < GA; ++a) nc[a] = 1;
     if (live > 0) {
         h = (float)pow(vol / target, 1.0 / (double)live);
         if (!(h > 0.f)) h = 1.0f;
@@ -71,7 +76,7 @@ __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int p
         for (int iter = 0; iter < 400; ++iter) {
             int64_t total = 1;
             bool fits = true;
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < GA; ++a) {
                 int c = 1;
                 if (a < g && ext[a] > 0.f) {
                     const float q = ext[a] / h;
@@ -84,20 +89,25 @@ __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int p
             h *= 1.15f;
         }
     }
-    gp->origin[0] = lo[0]; gp->origin[1] = lo[1]; gp->origin[2] = lo[2];
+    int ncells = 1;
+    for (int a = 0; a < GA; ++a) {
+        gp->origin[a] = lo[a];
+        gp->n[a] = nc[a];
+        ncells *= nc[a];
+    }
     gp->h = h;
     gp->inv_h = 1.0f / h;
-    gp->n[0] = nc[0]; gp->n[1] = nc[1]; gp->n[2] = nc[2];
-    gp->ncells = nc[0] * nc[1] * nc[2];
+    gp->ncells = ncells;
+    gp->g = g;
     gp->npts = n;
     gp->d = d;
 }
 
 __device__ __forceinline__ int cell_of_point(const float *p, int d, const GridParams &gp) {
-    int ix = cell_clamp(cell_coord(p[0], gp.origin[0], gp.inv_h), gp.n[0]);
-    int iy = d > 1 ? cell_clamp(cell_coord(p[1], gp.origin[1], gp.inv_h), gp.n[1]) : 0;
-    int iz = d > 2 ? cell_clamp(cell_coord(p[2], gp.origin[2], gp.inv_h), gp.n[2]) : 0;
-    return (iz * gp.n[1] + iy) * gp.n[0] + ix;
+    int c = 0;
+    for (int a = gp.g - 1; a >= 0; --a)
+        c = c * gp.n[a] + cell_clamp(cell_coord(p[a], gp.origin[a], gp.inv_h), gp.n[a]);
+    return c;
 }
 
 __global__ void cell_count_kernel(const float *__restrict__ pts, int64_t n, int d,

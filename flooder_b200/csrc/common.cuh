@@ -45,14 +45,22 @@ void count_launches(int n);
 // --------------------------------------------------------------------------------------
 // prepared cloud: layout of the workspace filled by flood_cloud_build_f32
 // --------------------------------------------------------------------------------------
-// Cell grid over the first min(d,3) axes.  Lives in DEVICE memory (head of the cloud
-// workspace) so that no host synchronisation is needed between building and using it.
+// Cell grid over the first min(d, kMaxGridAxes) axes (cubic cells; cell index = mixed radix with
+// axis 0 fastest).  Lives in DEVICE memory (head of the cloud workspace) so that no host
+// synchronisation is needed between building and using it.
+#ifndef FLOOD_MAX_GRID_AXES
+#define FLOOD_MAX_GRID_AXES 5
+#endif
+constexpr int kMaxGridAxes = FLOOD_MAX_GRID_AXES;
+__host__ __device__ constexpr int grid_axes(int d) { return d < kMaxGridAxes ? d : kMaxGridAxes; }
+
 struct GridParams {
-    float origin[3];   // lower corner of the cloud's bounding box
-    float inv_h;       // 1 / cell edge
+    float origin[kMaxGridAxes];   // lower corner of the cloud's bounding box
+    float inv_h;                  // 1 / cell edge
     float h;
-    int n[3];          // cells per axis (1 for unused axes)
-    int ncells;        // n[0]*n[1]*n[2]
+    int n[kMaxGridAxes];          // cells per axis (1 for unused axes)
+    int ncells;                   // product of n[]
+    int g;                        // binned axes
     int64_t npts;
     int d;
     int pad_;
@@ -68,7 +76,7 @@ __host__ __device__ constexpr int record_floats(int d) { return d <= 2 ? 2 : (d 
 
 struct CloudLayout {
     int64_t off_grid;        // GridParams
-    int64_t off_bbox;        // 6 x uint32 (ordered-int encoded min/max)
+    int64_t off_bbox;        // 2 x kMaxGridAxes x uint32 (ordered-int encoded min/max)
     int64_t off_cell_start;  // (max_cells + 1) x int32
     int64_t off_cell_fill;   // max_cells x int32 (scratch)
     int64_t off_cell_id;     // n x int32 (scratch)
@@ -90,7 +98,7 @@ __host__ __device__ inline CloudLayout cloud_layout(int64_t n, int d) {
     L.max_cells = cloud_max_cells(n);
     int64_t o = 0;
     L.off_grid = o;        o = align_up(o + (int64_t)sizeof(GridParams), 256);
-    L.off_bbox = o;        o = align_up(o + 8 * 4, 256);
+    L.off_bbox = o;        o = align_up(o + 2 * kMaxGridAxes * 4, 256);
     L.off_cell_start = o;  o = align_up(o + (L.max_cells + 1) * 4, 256);
     L.off_cell_fill = o;   o = align_up(o + L.max_cells * 4, 256);
     L.off_cell_id = o;     o = align_up(o + n * 4, 256);

@@ -42,18 +42,20 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // plan: tested[s] = length of the candidate stream of simplex s (one warp per simplex)
 // ---------------------------------------------------------------------------------------------
+template <int G>
 __global__ void cover_plan_kernel(CoverParams P, int d) {
     const GridParams gp = *P.gp;
     const int lane = threadIdx.x & 31;
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (warp >= P.S) return;
-    float c[FLOOD_MAX_DIM];
-    for (int a = 0; a < d; ++a) c[a] = P.centers[warp * d + a];
-    const BallCells b = ball_cells(c, P.radii[warp], d, gp);
+    float c[G];
+#pragma unroll
+    for (int a = 0; a < G; ++a) c[a] = P.centers[warp * d + a];
+    const BallCells<G> b = ball_cells<G>(c, P.radii[warp], gp);
     long long total = 0;
     for (int row = lane; row < b.nrows; row += 32) {
         int a, len;
-        row_run(b, row, gp, P.cell_start, a, len);
+        row_run<G>(b, row, gp, P.cell_start, a, len);
         total += len;
     }
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -68,6 +70,18 @@ __global__ void cover_plan_kernel(CoverParams P, int d) {
             const long long chunk2 = max((long long)P.chunk_seed, (long long)P.rows_per_chunk_factor * b.nrows);
             P.item_base_seed[warp] = (total + chunk2 - 1) / chunk2;
         }
+    }
+}
+
+void launch_plan(const CoverParams &P, int d, int64_t S, cudaStream_t st) {
+    const int threads = 128;  // 4 simplices per CTA
+    const unsigned blocks = (unsigned)((S * 32 + threads - 1) / threads);
+    switch (grid_axes(d)) {
+        case 1: cover_plan_kernel<1><<<blocks, threads, 0, st>>>(P, d); break;
+        case 2: cover_plan_kernel<2><<<blocks, threads, 0, st>>>(P, d); break;
+        case 3: cover_plan_kernel<3><<<blocks, threads, 0, st>>>(P, d); break;
+        case 4: cover_plan_kernel<4><<<blocks, threads, 0, st>>>(P, d); break;
+        default: cover_plan_kernel<kMaxGridAxes><<<blocks, threads, 0, st>>>(P, d); break;
     }
 }
 
@@ -149,9 +163,7 @@ int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, 
     P.S = S;
     P.chunk = 1;
     P.rows_per_chunk_factor = 0;
-    const int threads = 128;
-    const long long blocks = (S * 32 + threads - 1) / threads;
-    cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
+    launch_plan(P, d, S, st);
     count_launches(1);
     FLOOD_LAUNCH_CHECK("cover_plan_kernel");
     return FLOOD_OK;
@@ -163,11 +175,9 @@ int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, 
 int covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block) {
     if (R < 1 || d < 1 || d > FLOOD_MAX_DIM)
         return set_error(FLOOD_E_INVALID, "covering_bricks: bad arguments (R=%lld d=%d)", (long long)R, d);
-    const bool prune = get_option("prune", 1) != 0;
-    const ShapeDesc sd = kShapes[pick_shape(prune)];
-    const EvalShape sh = eval_shape(R, sd.maxt, sd.maxw);
-    const int total = sh.nsb * sh.W;
-    if (bricks_per_block) *bricks_per_block = sh.W;
+    const EvalShape sh = eval_shape(R, d);
+    const int total = sh.nsb * sh.nb;
+    if (bricks_per_block) *bricks_per_block = sh.nb;
     if (!out_groups) return total;
     if (capacity < total)
         return set_error(FLOOD_E_INVALID, "covering_bricks: capacity %d < %d bricks", capacity, total);
@@ -176,8 +186,11 @@ int covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *br
         int blk_groups = sh.groups - blk_g0;
         if (blk_groups > sh.groups_per_block) blk_groups = sh.groups_per_block;
         if (blk_groups < 0) blk_groups = 0;
-        const int g_base = blk_groups / sh.W, g_rem = blk_groups % sh.W;
-        for (int w = 0; w < sh.W; ++w) out_groups[sb * sh.W + w] = g_base + (w < g_rem ? 1 : 0);
+        for (int b = 0; b < sh.nb; ++b) {
+            int gf, gc;
+            brick_span(blk_groups, sh.nb, b, gf, gc);
+            out_groups[sb * sh.nb + b] = gc;
+        }
     }
     return total;
 }
@@ -252,9 +265,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
         fill_inf_kernel<<<blocks, 256, 0, st>>>(out_min_dist2, total);
     }
     {
-        const int threads = 128;  // 4 simplices per CTA
-        const long long blocks = (S * 32 + threads - 1) / threads;
-        cover_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, d);
+        launch_plan(P, d, S, st);
         cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base, S);
         if (P.item_base_seed) cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base_seed, S);
         count_launches(P.item_base_seed ? 4 : 3);   // fill, plan, scan (+ scan)

@@ -8,8 +8,10 @@ namespace flood {
 
 
 constexpr int kUnroll = 4;       // candidates per inner-loop trip
-constexpr int kAsyncLPL = 2;       // cp.async gather: records per lane and staging buffer
-constexpr int kBoundRefresh = 16;  // pruned sweep: candidates swept between refreshes of the warp bound
+// cp.async gather: records per lane and staging buffer (one for the 32-byte records of D >= 5)
+__host__ __device__ constexpr int async_lpl(int d) { return d <= 4 ? 2 : 1; }
+constexpr int kSurvivorFlush = 64;   // pruned sweep: survivors collected per warp before they are swept
+constexpr int kSurvivorBuf = kSurvivorFlush + 32;
 
 struct CoverParams {
     const GridParams *gp;
@@ -37,17 +39,27 @@ struct CoverParams {
     int nsb;                 // sample blocks per simplex
     int groups;              // ceil(R / 32) sample groups per simplex
     int groups_per_block;    // groups handled by one CTA pass (sample block)
+    int nb;                  // bricks per sample block (shared-memory resident)
+    int seg;                 // tile records per sweep task (work-stealing granularity)
     int tile_cap;            // candidate records per shared-memory tile
+    // dynamic shared memory layout (byte offsets; tile at 0)
+    int off_stage, off_wbuf, off_bricks, off_misc, off_runs;
     int chunk;               // target tested points per chunk
     int rows_per_chunk_factor;  // chunk >= factor * (cell rows of the simplex)
 };
 
 // ---------------------------------------------------------------------------------------------
-// geometry of a ball in cell coordinates
+// geometry of a ball in cell coordinates (G = number of binned axes, grid_axes(D))
 // ---------------------------------------------------------------------------------------------
+// A "row" is a line of cells along axis 0; the rows a ball touches are the cells of its footprint on
+// the other G-1 axes, numbered in memory order (axis 1 fastest).
+template <int G>
 struct BallCells {
-    float gx, gy, gz, gr2;
-    int iy0, iz0, nyb, nrows;
+    float g[G];                           // centre in cell coordinates
+    float gr2;                            // (inflated) squared radius in cells
+    int i0[G > 1 ? G : 2];                // first cell of the footprint on axes 1..G-1 (index 0 unused)
+    int nb[G > 1 ? G : 2];                // footprint extent on axes 1..G-1
+    int nrows;
 };
 
 __device__ __forceinline__ int clamp_cell(float v, int n) {
@@ -55,84 +67,118 @@ __device__ __forceinline__ int clamp_cell(float v, int n) {
     return (int)v;
 }
 
-__device__ __forceinline__ BallCells ball_cells(const float *c, float r, int d, const GridParams &gp) {
-    BallCells b;
-    b.gx = cell_coord(c[0], gp.origin[0], gp.inv_h);
-    b.gy = d > 1 ? cell_coord(c[1], gp.origin[1], gp.inv_h) : 0.5f;
-    b.gz = d > 2 ? cell_coord(c[2], gp.origin[2], gp.inv_h) : 0.5f;
+template <int G>
+__device__ __forceinline__ BallCells<G> ball_cells(const float *c, float r, const GridParams &gp) {
+    BallCells<G> b;
     // inflate: the cell mapping and the ball predicate are evaluated in float32
     const float gr = r * gp.inv_h * (1.0f + 1e-5f) + 2e-3f;
     b.gr2 = gr * gr;
-    int iy0 = max(0, clamp_cell(b.gy - gr, gp.n[1]));
-    int iy1 = min(gp.n[1] - 1, clamp_cell(b.gy + gr, gp.n[1]));
-    int iz0 = max(0, clamp_cell(b.gz - gr, gp.n[2]));
-    int iz1 = min(gp.n[2] - 1, clamp_cell(b.gz + gr, gp.n[2]));
-    b.iy0 = iy0;
-    b.iz0 = iz0;
-    b.nyb = max(0, iy1 - iy0 + 1);
-    b.nrows = b.nyb * max(0, iz1 - iz0 + 1);
+    b.nrows = 1;
+#pragma unroll
+    for (int a = 0; a < G; ++a) {
+        b.g[a] = cell_coord(c[a], gp.origin[a], gp.inv_h);
+        if (a > 0) {
+            const int lo = max(0, clamp_cell(b.g[a] - gr, gp.n[a]));
+            const int hi = min(gp.n[a] - 1, clamp_cell(b.g[a] + gr, gp.n[a]));
+            b.i0[a] = lo;
+            b.nb[a] = max(0, hi - lo + 1);
+            b.nrows *= b.nb[a];
+        }
+    }
     return b;
 }
 
-// run [a, a+len) of cell-sorted points covered by the ball in cell row `row` (rows are numbered
-// in memory order: y fastest, then z)
-__device__ __forceinline__ void row_run(const BallCells &b, int row, const GridParams &gp,
+// run [a, a+len) of cell-sorted points covered by the ball in cell row `row`
+template <int G>
+__device__ __forceinline__ void row_run(const BallCells<G> &b, int row, const GridParams &gp,
                                         const int *__restrict__ cell_start, int &a, int &len) {
-    const int iy = b.iy0 + row % b.nyb;
-    const int iz = b.iz0 + row / b.nyb;
-    const float dy = fmaxf(0.f, fmaxf((float)iy - b.gy, b.gy - (float)(iy + 1)));
-    const float dz = fmaxf(0.f, fmaxf((float)iz - b.gz, b.gz - (float)(iz + 1)));
-    const float rem = b.gr2 - dy * dy - dz * dz;
+    float rem = b.gr2;
+    int idx[G > 1 ? G : 2];
+#pragma unroll
+    for (int ax = 1; ax < G; ++ax) {
+        const int i = b.i0[ax] + row % b.nb[ax];
+        row /= b.nb[ax];
+        idx[ax] = i;
+        const float dd = fmaxf(0.f, fmaxf((float)i - b.g[ax], b.g[ax] - (float)(i + 1)));
+        rem -= dd * dd;
+    }
     a = 0;
     len = 0;
     if (rem < 0.f) return;
     const float half = sqrtf(rem);
-    const int ix0 = max(0, clamp_cell(b.gx - half, gp.n[0]));
-    const int ix1 = min(gp.n[0] - 1, clamp_cell(b.gx + half, gp.n[0]));
+    const int ix0 = max(0, clamp_cell(b.g[0] - half, gp.n[0]));
+    const int ix1 = min(gp.n[0] - 1, clamp_cell(b.g[0] + half, gp.n[0]));
     if (ix0 > ix1) return;
-    const int base = (iz * gp.n[1] + iy) * gp.n[0];
+    int base = 0;
+#pragma unroll
+    for (int ax = G - 1; ax >= 1; --ax) base = base * gp.n[ax] + idx[ax];
+    base *= gp.n[0];
     a = __ldg(cell_start + base + ix0);
     len = __ldg(cell_start + base + ix1 + 1) - a;
 }
 
-// Shape of a CTA pass: G sample groups over W warps (a multiple of 4, one set per SM
-// sub-partition), at most maxt groups per warp; more than maxw * maxt groups are split into nsb
-// sample blocks of (almost) equal size.
+// ---------------------------------------------------------------------------------------------
+// launch shapes
+// ---------------------------------------------------------------------------------------------
+// The samples of a simplex are cut into bricks of at most kMaxT groups of 32 samples; the bricks
+// of one sample block live in the shared memory of one CTA (nb bricks), more bricks than fit are
+// split into nsb sample blocks.  Two CTA shapes:
+//   wide    20 warps, 1 CTA per SM   (many bricks: every warp starts on its own brick)
+//   medium   8 warps, 2 CTAs per SM  } few bricks: independent CTAs overlap each other's gather and
+//   narrow   4 warps, 5 CTAs per SM  } sweep phases; the warps share the bricks segment by segment
+constexpr int kMaxT = 8;            // sample groups per brick (register-resident while swept)
+constexpr int kWideWarps = 20;
+constexpr int kMediumWarps = 8;
+constexpr int kMediumCtas = 2;
+constexpr int kNarrowWarps = 4;
+constexpr int kNarrowCtas = 5;
+constexpr int kMaxBricks = 20;      // bricks per CTA (<= 32: one lane per brick when stealing)
+
 struct EvalShape {
-    int W, nsb, groups, groups_per_block;
+    int W;        // warps per CTA
+    int minb;     // CTAs per SM the kernel is compiled for (1 or kNarrowCtas)
+    int nb;       // bricks per sample block
+    int nsb;      // sample blocks per simplex
+    int groups;   // ceil(R / 32)
+    int groups_per_block;
 };
 
-inline EvalShape eval_shape(int64_t R, int maxt, int maxw) {
-    const int G = (int)((R + 31) / 32);
-    auto warps_for = [&](int groups) {
-        if (groups < 4) return groups < 1 ? 1 : groups;
-        int w = (groups + maxt - 1) / maxt;
-        w = (w + 3) / 4 * 4;
-        return w > maxw ? maxw : w;
-    };
-    int forced = get_option("warps", 0);
-    if (forced < 0 || forced > maxw) forced = 0;
+// shared-memory bytes of one brick: kMaxT groups x (D coordinates + running minimum) x 32 lanes
+__host__ __device__ constexpr int brick_bytes(int d) { return kMaxT * (d + 1) * 32 * 4; }
+
+inline EvalShape eval_shape(int64_t R, int d) {
     EvalShape sh;
-    sh.W = forced ? forced : warps_for(G);
-    sh.nsb = (G + sh.W * maxt - 1) / (sh.W * maxt);
-    sh.groups = G;
-    sh.groups_per_block = (G + sh.nsb - 1) / sh.nsb;
-    if (!forced) sh.W = warps_for(sh.groups_per_block);
+    sh.groups = (int)((R + 31) / 32);
+    const int bricks = (sh.groups + kMaxT - 1) / kMaxT;
+    const int small_max = get_option("small_max_bricks", 2);
+    if (bricks <= small_max) {
+        const bool narrow = get_option("small_shape", 0) == 1;
+        sh.W = narrow ? kNarrowWarps : kMediumWarps;
+        sh.minb = narrow ? kNarrowCtas : kMediumCtas;
+        sh.nb = bricks;
+        sh.nsb = 1;
+    } else {
+        sh.W = kWideWarps;
+        sh.minb = 1;
+        int cap = (96 * 1024) / brick_bytes(d);          // at most 96 KB of samples per CTA
+        if (cap > kMaxBricks) cap = kMaxBricks;
+        if (cap < 1) cap = 1;
+        sh.nsb = (bricks + cap - 1) / cap;
+        sh.nb = 0;
+    }
+    sh.groups_per_block = (sh.groups + sh.nsb - 1) / sh.nsb;
+    if (sh.nb == 0) sh.nb = (sh.groups_per_block + kMaxT - 1) / kMaxT;
+    const int forced = get_option("warps", 0);
+    if (forced > 0 && forced <= (sh.minb == 1 ? kWideWarps : (sh.minb == kMediumCtas ? kMediumWarps : kNarrowWarps)))
+        sh.W = forced;
     return sh;
 }
 
-// Kernel shapes (template parameters MAXT, MAXW, MINB), selected with option "shape":
-//   0  (8, 20, 1)  wide: one CTA per SM holds all samples of a simplex (R <= 5120)
-//   1  (8,  4, 5)  narrow: sample blocks of 4 warps, five independent CTAs per SM
-//   2  (8,  8, 2)
-struct ShapeDesc {
-    int maxt, maxw, minb;
-};
-constexpr ShapeDesc kShapes[3] = {{8, 20, 1}, {8, 4, 5}, {8, 8, 2}};
-
-inline int pick_shape(bool prune) {
-    int sh = get_option("shape", prune ? 1 : 0);
-    return (sh < 0 || sh > 2) ? 0 : sh;
+// groups of brick b of a sample block with blk_groups groups dealt over nb bricks
+__host__ __device__ inline void brick_span(int blk_groups, int nb, int b, int &g_first, int &g_count) {
+    const int g_base = blk_groups / nb, g_rem = blk_groups % nb;
+    g_count = g_base + (b < g_rem ? 1 : 0);
+    g_first = b * g_base + (b < g_rem ? b : g_rem);
 }
 
 // 3-input minimum (FMNMX3 on sm_100a)
@@ -227,108 +273,6 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
     }
 }
 
-// Pruned sweep (exact).  The warp keeps the axis-aligned box of its sample points and the largest
-// of its running minima u.  A candidate whose distance to that box is at least sqrt(u) cannot lower
-// any of the warp's minima, so it is skipped: lanes test 32 tile records at a time against the
-// box, the survivors (ballot mask) go through the same 4-candidate packed body as sweep_tile.
-// u only shrinks, so a skip stays justified; the minima that come out are bit-identical to the
-// exhaustive sweep (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter
-// candidate rule" of SURVEY.md section 8(f2): the unit of work E is still counted by the
-// reference's ball rule, fewer evaluations are executed.
-template <int D, int NT_, int MAXT>
-__device__ __forceinline__ float sweep_tile_pruned(const typename Rec<D>::type *__restrict__ tile, int n,
-                                                  int sentinel_idx, const float (&x)[MAXT][D],
-                                                  float (&m)[MAXT], const float (&blo)[D],
-                                                  const float (&bhi)[D], int lane,
-                                                  unsigned long long &executed) {
-    auto bound = [&]() {
-        float u = m[0];
-#pragma unroll
-        for (int t = 1; t < NT_; ++t) u = fmaxf(u, m[t]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
-        return u;
-    };
-    float u = bound();
-    int pend0 = 0, pend1 = 0, pend2 = 0, npend = 0;
-    int stale = 0;   // candidates swept since u was last refreshed (a stale u is larger, i.e. still valid)
-#pragma unroll 1
-    for (int base = 0;; base += 32) {
-        const bool last = base >= n;   // one extra trip flushes the carried survivors
-        unsigned mask = 0u;
-        if (!last) {
-            const int idx = base + lane;
-            float own[D];
-            rec_unpack<D>(tile[idx < n ? idx : sentinel_idx], own);
-            float box2 = 0.f;
-#pragma unroll
-            for (int a = 0; a < D; ++a) {
-                const float e = fmaxf(fmaxf(blo[a] - own[a], own[a] - bhi[a]), 0.f);
-                box2 = fmaf(e, e, box2);
-            }
-            // 0.9999: the box distance and the pair distances are rounded differently
-            mask = __ballot_sync(0xffffffffu, idx < n && box2 * 0.9999f <= u);
-            if (mask == 0u) continue;
-            executed += (unsigned)__popc(mask);
-        }
-        // survivors are swept four at a time; fewer than four are carried over to the next block
-        // (pend0..2, warp-uniform) so that the packed body runs on full groups
-        while (npend + __popc(mask) >= kUnroll || (last && npend > 0)) {
-            float p[kUnroll][D];
-#pragma unroll
-            for (int v = 0; v < kUnroll; ++v) {
-                int j = sentinel_idx;
-                if (v < npend) {
-                    j = v == 0 ? pend0 : (v == 1 ? pend1 : pend2);
-                } else if (mask) {
-                    j = base + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                }
-                rec_unpack<D>(tile[j], p[v]);
-            }
-            npend = 0;
-            stale += kUnroll;
-#pragma unroll
-            for (int v0 = 0; v0 < kUnroll; v0 += 2) {
-#pragma unroll
-                for (int t = 0; t + 1 < NT_; t += 2) {
-                    float2 acc[2];
-#pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        float2 df = __fadd2_rn(make_float2(x[t][0], x[t + 1][0]),
-                                               make_float2(-p[v0 + v][0], -p[v0 + v][0]));
-                        acc[v] = __fmul2_rn(df, df);
-#pragma unroll
-                        for (int a = 1; a < D; ++a) {
-                            df = __fadd2_rn(make_float2(x[t][a], x[t + 1][a]),
-                                            make_float2(-p[v0 + v][a], -p[v0 + v][a]));
-                            acc[v] = __ffma2_rn(df, df, acc[v]);
-                        }
-                    }
-                    m[t] = fmin3(m[t], acc[0].x, acc[1].x);
-                    m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
-                }
-                if (NT_ & 1) {
-                    constexpr int t = NT_ - 1;
-                    m[t] = fmin3(m[t], dist2<D>(x[t], p[v0]), dist2<D>(x[t], p[v0 + 1]));
-                }
-            }
-        }
-        while (mask) {
-            const int jn = base + __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (npend == 0) pend0 = jn; else if (npend == 1) pend1 = jn; else pend2 = jn;
-            ++npend;
-        }
-        if (stale >= kBoundRefresh) {
-            u = bound();
-            stale = 0;
-        }
-        if (last) break;
-    }
-    return stale ? bound() : u;
-}
-
 // last i in [0, n) with pos[i] <= p, for a non-decreasing pos[] with pos[0] <= p.  Warp-uniform
 // two-level ballot search (two shared-memory rounds instead of a log2(n) dependent chain).
 __device__ __forceinline__ int find_run(const int *pos, int n, int p, int lane) {
@@ -339,313 +283,136 @@ __device__ __forceinline__ int find_run(const int *pos, int n, int p, int lane) 
     return c * step + __popc(__ballot_sync(0xffffffffu, lane < step && ib < n && pos[ib] <= p)) - 1;
 }
 
-// MAXT = sample groups per warp held in registers, MAXW = warps per CTA, MINB = CTAs per SM the
-// register budget is sized for.  (8, 20, 1) is the wide shape: one CTA per SM holds every sample
-// of a simplex.  (8, 4, 5) splits the samples of a simplex over sample blocks of 4 warps: five
-// independent CTAs per SM (one warp per sub-partition each), so a warp that waits at a CTA
-// barrier for a slower one leaves the issue slots to the other CTAs.
-template <int D, bool PRUNE, int MAXT, int MAXW, int MINB>
-__global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
-    constexpr int kMaxT = MAXT;
-    constexpr int LPL = D <= 4 ? 4 : 2;  // records in flight per lane while gathering
-    constexpr int UNIT = 32 * LPL;       // stream positions per warp work unit
-    constexpr int ALPL = kAsyncLPL;      // the same for the cp.async path (staged in shared memory)
-    constexpr int AUNIT = 32 * ALPL;
+// ---------------------------------------------------------------------------------------------
+// candidate stream of one work item -> shared-memory tile
+// ---------------------------------------------------------------------------------------------
+// Rows of the ball -> runs of the cell-sorted cloud, NT rows at a time; the runs of a batch (clipped
+// to the item's window of the stream) are gathered by the warps in units of consecutive stream
+// positions: coalesced record loads (cp.async double-buffered through a per-warp staging ring, or
+// plain loads), the reference's ball test, an optional CTA-level cull, warp-ballot compaction
+// into the tile.
+template <int D>
+struct Stream {
     using RecT = typename Rec<D>::type;
+    static constexpr int LPL = D <= 4 ? 4 : 2;   // plain loads: records in flight per lane
+    static constexpr int UNIT = 32 * LPL;
+    static constexpr int ALPL = async_lpl(D);    // cp.async: records per lane and staging buffer
+    static constexpr int AUNIT = 32 * ALPL;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = blockDim.x;
-    const int tile_cap = P.tile_cap;
-    RecT *tile = reinterpret_cast<RecT *>(smem_raw);
-    // per-warp staging ring of the cp.async gather: 2 buffers x AUNIT records
-    RecT *stage = tile + (tile_cap + kUnroll) + (size_t)(threadIdx.x >> 5) * (P.async_gather ? 2 * AUNIT : 0);
-    int *run_start = reinterpret_cast<int *>(smem_raw + (size_t)(tile_cap + kUnroll) * sizeof(RecT) +
-                                             (P.async_gather ? (size_t)(NT >> 5) * 2 * AUNIT * sizeof(RecT) : 0));
-    int *run_pos = run_start + NT;
-    __shared__ int warp_sums[32];
-    __shared__ int s_fill;
-    __shared__ long long s_item[3];          // simplex, chunk, sample block (-1 = queue drained)
-    __shared__ float s_wbox[MAXW][2 * D];    // per-warp sample boxes (pruned mode)
-    __shared__ float s_wu[MAXW];             // per-warp largest running minimum
-    __shared__ float s_cbox[2 * D + 1];      // box of all samples of the CTA, and the CTA-wide bound
+    // per CTA (shared memory / constants)
+    const RecT *points;
+    RecT *tile, *stage;          // stage: this warp's ring of 2 x AUNIT records
+    int *run_start, *run_pos, *warp_sums, *s_fill;
+    const float *s_cbox;         // [2D] box of the CTA's samples (cull)
+    const int *cell_start;
+    const GridParams *gp;
+    int tile_cap, stride, async_gather;
+    // per item
+    BallCells<grid_axes(D)> bc;
+    float c[D], r2;
+    int win_lo, win_hi;
+    int rb, carry, q0, total2;
+    bool done;
+    unsigned inball;             // records inside the ball seen by this warp (lane-uniform)
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = NT >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const GridParams gp = *P.gp;
-    const RecT *__restrict__ points = reinterpret_cast<const RecT *>(P.points);
-    const long long total_chunks = P.item_base[P.S];
-    const unsigned long long total_items = (unsigned long long)total_chunks * (unsigned)P.nsb;
-    const int stride = P.stream_stride;
+    __device__ __forceinline__ void begin(const BallCells<grid_axes(D)> &b, const float (&centre)[D], float radius2, int lo, int hi) {
+        bc = b;
+#pragma unroll
+        for (int a = 0; a < D; ++a) c[a] = centre[a];
+        r2 = radius2;
+        win_lo = lo;
+        win_hi = hi;
+        rb = carry = q0 = total2 = 0;
+        done = false;
+        inball = 0;
+    }
 
-    if (tid == 0) s_fill = 0;
-    if (tid < kUnroll) tile[tile_cap + tid] = rec_sentinel<D>();   // never overwritten (pruned sweeps pad with them)
-    unsigned long long executed_evals = 0;   // evaluations this warp performed in the whole launch
-
-    for (;;) {
-        // ---- fetch a work item ---------------------------------------------------------------
-        __syncthreads();  // previous item fully retired (s_item, tile, run arrays reusable)
-        if (tid == 0) {
-            const unsigned long long g = atomicAdd(P.queue, 1ull);
-            if (g >= total_items) {
-                s_item[0] = -1;
-            } else {
-                const long long gi = (long long)(g / (unsigned)P.nsb);
-                long long lo = 0, hi = P.S;  // last s with item_base[s] <= gi
-                while (hi - lo > 1) {
-                    const long long mid = (lo + hi) >> 1;
-                    if (P.item_base[mid] <= gi) lo = mid; else hi = mid;
+    // ball test (+ cull against the CTA's sample box) of up to N records per lane, compaction
+    template <bool CULL, typename RecArray>
+    __device__ __forceinline__ void test_and_compact(RecArray &rec, int nrec, float U, int lane) {
+        constexpr int N = sizeof(rec) / sizeof(rec[0]);
+        const unsigned lt_mask = (1u << lane) - 1u;
+        unsigned keep[N];
+        int nkeep = 0;
+#pragma unroll
+        for (int v = 0; v < N; ++v) {
+            bool pass = false, near = false;
+            if (lane + 32 * v < nrec) {
+                float q[D];
+                rec_unpack<D>(rec[v], q);
+                // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
+                float t = q[0] - c[0];
+                float acc = t * t;
+#pragma unroll
+                for (int a2 = 1; a2 < D; ++a2) {
+                    t = q[a2] - c[a2];
+                    acc = fmaf(t, t, acc);
                 }
-                s_item[0] = lo;
-                s_item[1] = gi - P.item_base[lo];
-                s_item[2] = (long long)(g % (unsigned)P.nsb);
-            }
-        }
-        __syncthreads();
-        const long long s = s_item[0];
-        if (s < 0) break;
-        const long long chunk_j = s_item[1];
-        const int sb = (int)s_item[2];
-
-        // ---- simplex constants ---------------------------------------------------------------
-        float c[D];
+                pass = acc <= r2;
+                if (CULL && pass) {
+                    // a record at least sqrt(U) away from the box of the CTA's samples cannot
+                    // lower any of their minima
+                    float box2 = 0.f;
 #pragma unroll
-        for (int a = 0; a < D; ++a) c[a] = __ldg(P.centers + s * D + a);
-        const float rad = __ldg(P.radii + s);
-        const float r2 = rad * rad;
-        const BallCells bc = ball_cells(c, rad, D, gp);
-        const long long tested = P.tested[s];
-        const long long nch = P.item_base[s + 1] - P.item_base[s];
-        const int win_lo = (int)(chunk_j * tested / nch);
-        const int win_hi = (int)((chunk_j + 1) * tested / nch);
-
-        // ---- this warp's sample groups ---------------------------------------------------------
-        // The sample block's groups (32 consecutive samples each) are dealt to the warps as evenly
-        // as possible; consecutive warps sit on different SM sub-partitions, so the sub-partition
-        // loads differ by at most one group.  (flood_covering_bricks reports this layout, so the
-        // host can order the samples such that every warp holds a compact brick.)
-        const int blk_g0 = sb * P.groups_per_block;
-        const int blk_groups = min(P.groups_per_block, P.groups - blk_g0);
-        const int g_base = blk_groups / W, g_rem = blk_groups % W;
-        const int nt = g_base + (warp < g_rem ? 1 : 0);
-        const int g0 = blk_g0 + warp * g_base + min(warp, g_rem);
-        float x[kMaxT][D], m[kMaxT];
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-            const long long r = (long long)(g0 + t) * 32 + lane;
-            // pruned mode starts from what other chunks / the seed pass already found (an upper
-            // bound of the minimum); unused slots carry 0 so that they never loosen the warp bound
-            m[t] = PRUNE ? 0.f : INFINITY;
-            if (PRUNE && t < nt && r < P.R) m[t] = __ldcg(P.out + s * P.R + r);
-#pragma unroll
-            for (int a = 0; a < D; ++a) x[t][a] = c[a];
-        }
-        if (P.samples) {
-#pragma unroll
-            for (int t = 0; t < kMaxT; ++t) {
-                const long long r = (long long)(g0 + t) * 32 + lane;
-                if (t < nt && r < P.R) {
-#pragma unroll
-                    for (int a = 0; a < D; ++a) x[t][a] = __ldg(P.samples + (s * P.R + r) * D + a);
-                }
-            }
-        } else {
-            // x = sum_k w[r,k] * v[s,k,:], FMA chain over k ascending (== the reference's float32
-            // matmul, core.py:188); k is the outer loop so that a vertex is loaded once per warp
-#pragma unroll 1
-            for (int k = 0; k < P.K; ++k) {
-                float v[D];
-#pragma unroll
-                for (int a = 0; a < D; ++a) v[a] = __ldg(P.verts + (s * P.K + k) * D + a);
-#pragma unroll
-                for (int t = 0; t < kMaxT; ++t) {
-                    const long long r = (long long)(g0 + t) * 32 + lane;
-                    if (t < nt && r < P.R) {
-                        const float wk = __ldg(P.weights + r * P.K + k);
-#pragma unroll
-                        for (int a = 0; a < D; ++a)
-                            x[t][a] = k == 0 ? __fmul_rn(wk, v[a]) : fmaf(wk, v[a], x[t][a]);
+                    for (int a2 = 0; a2 < D; ++a2) {
+                        const float e2 = fmaxf(fmaxf(s_cbox[a2] - q[a2], q[a2] - s_cbox[D + a2]), 0.f);
+                        box2 = fmaf(e2, e2, box2);
                     }
+                    near = box2 * 0.9999f <= U;
                 }
             }
+            const unsigned bm = __ballot_sync(0xffffffffu, pass);
+            inball += (unsigned)__popc(bm);
+            keep[v] = CULL ? __ballot_sync(0xffffffffu, near) : bm;
+            nkeep += __popc(keep[v]);
         }
-
-        // boxes and bounds (pruned mode): per warp in registers, per CTA in shared memory
-        float blo[D], bhi[D];
-        float U = INFINITY;   // CTA-wide: the largest running minimum of any sample of the CTA
-        if (PRUNE) {
+        int wbase = 0;
+        if (lane == 0 && nkeep) wbase = atomicAdd(s_fill, nkeep);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
 #pragma unroll
-            for (int a = 0; a < D; ++a) {
-                float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-                for (int t = 0; t < kMaxT; ++t) {
-                    const long long r = (long long)(g0 + t) * 32 + lane;
-                    if (t < nt && r < P.R) { lo = fminf(lo, x[t][a]); hi = fmaxf(hi, x[t][a]); }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-                }
-                blo[a] = lo;
-                bhi[a] = hi;
-                if (lane == 0) { s_wbox[warp][a] = lo; s_wbox[warp][D + a] = hi; }
-            }
-            float u = m[0];
-#pragma unroll
-            for (int t = 1; t < kMaxT; ++t) u = fmaxf(u, m[t]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
-            if (lane == 0) s_wu[warp] = u;
-            __syncthreads();
-            if (tid <= 2 * D) {
-                float v;
-                if (tid < D) { v = INFINITY; for (int w = 0; w < W; ++w) v = fminf(v, s_wbox[w][tid]); }
-                else if (tid < 2 * D) { v = -INFINITY; for (int w = 0; w < W; ++w) v = fmaxf(v, s_wbox[w][tid]); }
-                else { v = 0.f; for (int w = 0; w < W; ++w) v = fmaxf(v, s_wu[w]); }
-                s_cbox[tid] = v;
-            }
-            __syncthreads();
-            U = s_cbox[2 * D];
+        for (int v = 0; v < N; ++v) {
+            if ((keep[v] >> lane) & 1u) tile[wbase + __popc(keep[v] & lt_mask)] = rec[v];
+            wbase += __popc(keep[v]);
         }
+    }
 
-        unsigned long long executed = 0;   // candidate records this warp swept in the current item
-        auto sweep = [&](int n) __attribute__((always_inline)) {
-            // on entry: the tile holds n records and every thread is past the barrier that
-            // completed it; on exit: the tile is empty and reusable
-            if (PRUNE) {
-                float u = 0.f;
-                switch (nt) {  // warp-uniform
-                    case 1: if constexpr (1 <= MAXT) u = sweep_tile_pruned<D, 1, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 2: if constexpr (2 <= MAXT) u = sweep_tile_pruned<D, 2, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 3: if constexpr (3 <= MAXT) u = sweep_tile_pruned<D, 3, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 4: if constexpr (4 <= MAXT) u = sweep_tile_pruned<D, 4, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 5: if constexpr (5 <= MAXT) u = sweep_tile_pruned<D, 5, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 6: if constexpr (6 <= MAXT) u = sweep_tile_pruned<D, 6, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 7: if constexpr (7 <= MAXT) u = sweep_tile_pruned<D, 7, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    case 8: if constexpr (8 <= MAXT) u = sweep_tile_pruned<D, 8, MAXT>(tile, n, tile_cap, x, m, blo, bhi, lane, executed); break;
-                    default: break;
+    // Gather until the tile cannot take another round or the stream is exhausted (done).  Every
+    // thread of the CTA calls it; on return all threads are past the barrier that completed the
+    // tile.  Returns the new fill.
+    template <bool CULL>
+    __device__ __forceinline__ int fill_tile(int fill, float U) {
+        const int NT = blockDim.x, W = NT >> 5;
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        while (!done) {
+            if (q0 >= total2) {
+                // next batch of NT rows -> runs
+                if (rb >= bc.nrows || carry >= win_hi) {
+                    done = true;
+                    break;
                 }
-                if (lane == 0) s_wu[warp] = u;
+                const int row = rb + tid;
+                rb += NT;
+                int a = 0, len = 0;
+                if (row < bc.nrows) row_run(bc, row, *gp, cell_start, a, len);
+                int batch_total;
+                const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
+                carry += batch_total;
+                q0 = total2 = 0;
+                if (carry <= win_lo) continue;
+                // clip the run to this item's window of the stream; a seed pass (stride > 1) takes
+                // every stride-th record of each clipped run
+                const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
+                const int len2 = max(0, s1 - s0);
+                const int pos2 = block_exclusive_scan((len2 + stride - 1) / stride, warp_sums, total2);
+                run_start[tid] = a + (s0 - off);
+                run_pos[tid] = pos2;
+                if (tid == 0) run_pos[NT] = total2;
                 __syncthreads();
-                if (tid == 0) s_fill = 0;
-                float cu = 0.f;
-                for (int w = 0; w < W; ++w) cu = fmaxf(cu, s_wu[w]);
-                U = cu;
-                __syncthreads();
-                return;
+                continue;
             }
-            const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
-            if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
-            __syncthreads();
-            switch (nt) {  // warp-uniform
-                case 1: if constexpr (1 <= MAXT) sweep_tile<D, 1, MAXT>(tile, npad, x, m); break;
-                case 2: if constexpr (2 <= MAXT) sweep_tile<D, 2, MAXT>(tile, npad, x, m); break;
-                case 3: if constexpr (3 <= MAXT) sweep_tile<D, 3, MAXT>(tile, npad, x, m); break;
-                case 4: if constexpr (4 <= MAXT) sweep_tile<D, 4, MAXT>(tile, npad, x, m); break;
-                case 5: if constexpr (5 <= MAXT) sweep_tile<D, 5, MAXT>(tile, npad, x, m); break;
-                case 6: if constexpr (6 <= MAXT) sweep_tile<D, 6, MAXT>(tile, npad, x, m); break;
-                case 7: if constexpr (7 <= MAXT) sweep_tile<D, 7, MAXT>(tile, npad, x, m); break;
-                case 8: if constexpr (8 <= MAXT) sweep_tile<D, 8, MAXT>(tile, npad, x, m); break;
-                default: break;
-            }
-            executed += (unsigned)n;
-            __syncthreads();
-            if (tid == 0) s_fill = 0;
-            __syncthreads();
-        };
-
-        // ball test (+ CTA-level cull) of up to N records per lane, warp-ballot compaction into the tile
-        unsigned inball = 0;   // records inside the ball seen by this warp (lane-uniform)
-        auto test_and_compact = [&](auto &rec, int nrec) __attribute__((always_inline)) {
-            constexpr int N = sizeof(rec) / sizeof(rec[0]);
-            unsigned keep[N];
-            int nkeep = 0;
-#pragma unroll
-            for (int v = 0; v < N; ++v) {
-                bool pass = false, near = false;
-                if (lane + 32 * v < nrec) {
-                    float q[D];
-                    rec_unpack<D>(rec[v], q);
-                    // the reference predicate (triton_kernels.py:137-148): sum (p-c)^2 <= r^2
-                    float t = q[0] - c[0];
-                    float acc = t * t;
-#pragma unroll
-                    for (int a2 = 1; a2 < D; ++a2) {
-                        t = q[a2] - c[a2];
-                        acc = fmaf(t, t, acc);
-                    }
-                    pass = acc <= r2;
-                    if (PRUNE && pass) {
-                        // CTA-level cull: a record at least sqrt(U) away from the box of the CTA's
-                        // samples cannot lower any of their minima
-                        float box2 = 0.f;
-#pragma unroll
-                        for (int a2 = 0; a2 < D; ++a2) {
-                            const float e2 = fmaxf(fmaxf(s_cbox[a2] - q[a2], q[a2] - s_cbox[D + a2]), 0.f);
-                            box2 = fmaf(e2, e2, box2);
-                        }
-                        near = box2 * 0.9999f <= U;
-                    }
-                }
-                const unsigned bm = __ballot_sync(0xffffffffu, pass);
-                inball += (unsigned)__popc(bm);
-                keep[v] = PRUNE ? __ballot_sync(0xffffffffu, near) : bm;
-                nkeep += __popc(keep[v]);
-            }
-            int wbase = 0;
-            if (lane == 0 && nkeep) wbase = atomicAdd(&s_fill, nkeep);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-            for (int v = 0; v < N; ++v) {
-                if ((keep[v] >> lane) & 1u) tile[wbase + __popc(keep[v] & lt_mask)] = rec[v];
-                wbase += __popc(keep[v]);
-            }
-        };
-
-        // ---- stream the candidate window -----------------------------------------------------
-        // Rows of the ball -> runs of the cell-sorted cloud, NT rows at a time; the runs of a
-        // batch (clipped to this item's window of the stream) are gathered by the warps in units
-        // of UNIT consecutive stream positions: coalesced record loads, ball test, warp-ballot
-        // compaction into the tile.  The tile is swept whenever the next round might overflow it.
-        int fill = 0;
-        int carry = 0;         // stream offset of the next row batch
-        int rb = 0;            // first row of the next row batch
-        int q0 = 0, total2 = 0;  // progress inside the current row batch (stream positions)
-        bool stream_done = false;
-        // One sweep call site (the sweep is instantiated for every group count): alternate between
-        // "gather until the tile cannot take the next round" and "sweep".
-        for (;;) {
-            while (!stream_done) {
-                if (q0 >= total2) {
-                    // next batch of NT rows -> runs
-                    if (rb >= bc.nrows || carry >= win_hi) {
-                        stream_done = true;
-                        break;
-                    }
-                    const int row = rb + tid;
-                    rb += NT;
-                    int a = 0, len = 0;
-                    if (row < bc.nrows) row_run(bc, row, gp, P.cell_start, a, len);
-                    int batch_total;
-                    const int off = carry + block_exclusive_scan(len, warp_sums, batch_total);
-                    carry += batch_total;
-                    q0 = total2 = 0;
-                    if (carry <= win_lo) continue;
-                    // clip the run to this chunk's window of the stream; a seed pass (stride > 1)
-                    // takes every stride-th record of each clipped run
-                    const int s0 = max(off, win_lo), s1 = min(off + len, win_hi);
-                    const int len2 = max(0, s1 - s0);
-                    const int pos2 = block_exclusive_scan((len2 + stride - 1) / stride, warp_sums, total2);
-                    run_start[tid] = a + (s0 - off);
-                    run_pos[tid] = pos2;
-                    if (tid == 0) run_pos[NT] = total2;
-                    __syncthreads();
-                    continue;
-                }
-                if (fill > 0 && tile_cap - fill < min(total2 - q0, UNIT * W)) break;   // tile full: sweep first
+            if (fill > 0 && tile_cap - fill < min(total2 - q0, UNIT * W)) break;   // tile full: sweep first
             const int take = min(total2 - q0, tile_cap - fill);
-            if (P.async_gather) {
+            if (async_gather) {
                 // cp.async (LDGSTS) double buffering: the records of the warp's next unit are in
                 // flight to its staging buffer while the current unit is tested and compacted
                 const int nunits = (take + AUNIT - 1) / AUNIT;
@@ -683,7 +450,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
 #pragma unroll
                     for (int v = 0; v < ALPL; ++v)
                         if (lane + 32 * v < n_cur) rec[v] = stage[buf * AUNIT + lane + 32 * v];
-                    test_and_compact(rec, n_cur);
+                    test_and_compact<CULL>(rec, n_cur, U, lane);
                     __syncwarp();   // every lane has read the buffer before it is refilled
                     unit = next;
                     buf ^= 1;
@@ -706,65 +473,425 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             const int k = lane + 32 * v;
                             if (k < nrec) rec[v] = rec_ldg<D>(src + (long long)k * stride);
                         }
-                        test_and_compact(rec, nrec);
+                        test_and_compact<CULL>(rec, nrec, U, lane);
                         p += nrec;
                     }
                 }
             }
-                __syncthreads();
-                fill = s_fill;
-                q0 += take;
+            __syncthreads();
+            fill = *s_fill;
+            q0 += take;
+        }
+        return fill;
+    }
+};
+
+// sweep of n (a multiple of kUnroll) records by a warp holding nt sample groups (warp-uniform)
+template <int D>
+__device__ __forceinline__ void sweep_records(const typename Rec<D>::type *recs, int n, int nt,
+                                              const float (&x)[kMaxT][D], float (&m)[kMaxT]) {
+    switch (nt) {
+        case 1: sweep_tile<D, 1, kMaxT>(recs, n, x, m); break;
+        case 2: sweep_tile<D, 2, kMaxT>(recs, n, x, m); break;
+        case 3: sweep_tile<D, 3, kMaxT>(recs, n, x, m); break;
+        case 4: sweep_tile<D, 4, kMaxT>(recs, n, x, m); break;
+        case 5: sweep_tile<D, 5, kMaxT>(recs, n, x, m); break;
+        case 6: sweep_tile<D, 6, kMaxT>(recs, n, x, m); break;
+        case 7: sweep_tile<D, 7, kMaxT>(recs, n, x, m); break;
+        case 8: sweep_tile<D, 8, kMaxT>(recs, n, x, m); break;
+        default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent evaluation kernel
+// ---------------------------------------------------------------------------------------------
+// Work item = (simplex, chunk of its candidate stream, sample block), pulled from a global atomic
+// queue.  Per item the CTA alternates between two phases:
+//
+//   gather  all warps stream the item's window of the candidate stream into the tile (Stream);
+//   sweep   the tile is cut into segments of P.seg records; (brick, segment) pairs are the tasks.
+//           A warp starts on "its" brick (warp % nb), claims segments from the brick's cursor
+//           (shared-memory atomic) and, when the brick has none left, steals from the brick with
+//           the most unclaimed segments.  While it works on a brick the warp holds the brick's
+//           sample coordinates and running minima in registers (loaded from / merged back into
+//           shared memory with atomicMin), so the inner loop is sweep_tile: broadcast LDS.128 of
+//           the records, packed FP32x2 arithmetic, FMNMX3.
+//
+// PRUNE (default) skips work exactly: per task the warp tests the segment's records, 32 at a
+// time, against the bounding box of the brick's samples -- a record at least as far from the box
+// as the brick's largest running minimum u cannot lower any minimum -- and collects the survivors
+// in a per-warp buffer that is swept kSurvivorFlush records at a time.  u only shrinks, so a skip
+// stays justified; the minima are bit-identical to the exhaustive sweep
+// (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter candidate rule" of
+// the unit of work E is still counted by the reference's ball rule, fewer
+// evaluations are executed.  The same bound, taken over all bricks of the CTA, culls records
+// before they enter the tile.
+template <int D, bool PRUNE, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
+    using RecT = typename Rec<D>::type;
+    using StreamT = Stream<D>;
+    constexpr int XS = (D + 1) * 32;           // floats per (brick, group): D coordinate rows + the minima row
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = NT >> 5;
+    const int nb = P.nb;
+    const int tile_cap = P.tile_cap;
+    RecT *tile = reinterpret_cast<RecT *>(smem_raw);
+    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * kSurvivorBuf;
+    float *bricks = reinterpret_cast<float *>(smem_raw + P.off_bricks);       // [nb][kMaxT][D+1][32]
+    float *sbox = reinterpret_cast<float *>(smem_raw + P.off_misc);           // [nb][2D]
+    unsigned *ub = reinterpret_cast<unsigned *>(sbox + nb * 2 * D);           // [nb] largest minimum per brick
+    int *cursor = reinterpret_cast<int *>(ub + nb);                           // [nb] next unclaimed segment
+    int *run_start = reinterpret_cast<int *>(smem_raw + P.off_runs);
+    __shared__ int warp_sums[32];
+    __shared__ int s_fill;
+    __shared__ long long s_item[3];          // simplex, chunk, sample block (-1 = queue drained)
+    __shared__ float s_cbox[2 * D + 1];      // box of all samples of the CTA, and the CTA-wide bound
+    __shared__ GridParams s_gp;
+
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long total_chunks = P.item_base[P.S];
+    const unsigned long long total_items = (unsigned long long)total_chunks * (unsigned)P.nsb;
+
+    StreamT st;
+    st.points = reinterpret_cast<const RecT *>(P.points);
+    st.tile = tile;
+    st.stage = reinterpret_cast<RecT *>(smem_raw + P.off_stage) + (size_t)warp * 2 * StreamT::AUNIT;
+    st.run_start = run_start;
+    st.run_pos = run_start + NT;
+    st.warp_sums = warp_sums;
+    st.s_fill = &s_fill;
+    st.s_cbox = s_cbox;
+    st.cell_start = P.cell_start;
+    st.gp = &s_gp;
+    st.tile_cap = tile_cap;
+    st.stride = P.stream_stride;
+    st.async_gather = P.async_gather;
+
+    if (tid == 0) {
+        s_fill = 0;
+        s_gp = *P.gp;
+    }
+    if (tid < kUnroll) tile[tile_cap + tid] = rec_sentinel<D>();   // never overwritten
+    unsigned long long executed_evals = 0;   // evaluations this warp performed in the whole launch
+
+    for (;;) {
+        // ---- fetch a work item ---------------------------------------------------------------
+        __syncthreads();  // previous item fully retired (s_item, tile, bricks, run arrays reusable)
+        if (tid == 0) {
+            const unsigned long long g = atomicAdd(P.queue, 1ull);
+            if (g >= total_items) {
+                s_item[0] = -1;
+            } else {
+                const long long gi = (long long)(g / (unsigned)P.nsb);
+                long long lo = 0, hi = P.S;  // last s with item_base[s] <= gi
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (P.item_base[mid] <= gi) lo = mid; else hi = mid;
+                }
+                s_item[0] = lo;
+                s_item[1] = gi - P.item_base[lo];
+                s_item[2] = (long long)(g % (unsigned)P.nsb);
             }
+        }
+        __syncthreads();
+        const long long s = s_item[0];
+        if (s < 0) break;
+        const long long chunk_j = s_item[1];
+        const int sb = (int)s_item[2];
+
+        // ---- simplex constants ---------------------------------------------------------------
+        float c[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) c[a] = __ldg(P.centers + s * D + a);
+        const float rad = __ldg(P.radii + s);
+        {
+            const long long tested = P.tested[s];
+            const long long nch = P.item_base[s + 1] - P.item_base[s];
+            st.begin(ball_cells<grid_axes(D)>(c, rad, s_gp), c, rad * rad, (int)(chunk_j * tested / nch),
+                     (int)((chunk_j + 1) * tested / nch));
+        }
+
+        // ---- the sample block's bricks -> shared memory ----------------------------------------
+        // Groups of 32 consecutive samples are dealt to the bricks as evenly as possible
+        // (flood_covering_bricks reports this layout, so the host can order the samples such that
+        // every brick is spatially compact).  Row a < D of a group holds coordinate a of its 32
+        // samples, row D their running minima (pruned mode starts from what other chunks / the
+        // seed pass already found; unused slots carry 0 so that they never loosen a bound).
+        const int blk_g0 = sb * P.groups_per_block;
+        const int blk_groups = min(P.groups_per_block, P.groups - blk_g0);
+        for (int b = warp; b < nb; b += W) {
+            int gf, gc;
+            brick_span(blk_groups, nb, b, gf, gc);
+            float lo[D], hi[D], u = 0.f;
+#pragma unroll
+            for (int a = 0; a < D; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+            for (int t = 0; t < kMaxT; ++t) {
+                const long long r = (long long)(blk_g0 + gf + t) * 32 + lane;
+                const bool valid = t < gc && r < P.R;
+                float x[D], mval = PRUNE ? 0.f : INFINITY;
+#pragma unroll
+                for (int a = 0; a < D; ++a) x[a] = c[a];
+                if (valid) {
+                    if (PRUNE) mval = __ldcg(P.out + s * P.R + r);
+                    if (P.samples) {
+#pragma unroll
+                        for (int a = 0; a < D; ++a) x[a] = __ldg(P.samples + (s * P.R + r) * D + a);
+                    } else {
+                        // x = sum_k w[r,k] * v[s,k,:], FMA chain over k ascending (== the reference's
+                        // float32 matmul, core.py:188)
+                        const float *w = P.weights + r * P.K;
+                        const float *v = P.verts + s * P.K * D;
+                        const float w0 = __ldg(w);
+#pragma unroll
+                        for (int a = 0; a < D; ++a) x[a] = __fmul_rn(w0, __ldg(v + a));
+                        for (int k = 1; k < P.K; ++k) {
+                            const float wk = __ldg(w + k);
+#pragma unroll
+                            for (int a = 0; a < D; ++a) x[a] = fmaf(wk, __ldg(v + k * D + a), x[a]);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < D; ++a) { lo[a] = fminf(lo[a], x[a]); hi[a] = fmaxf(hi[a], x[a]); }
+                }
+                float *g = bricks + ((size_t)b * kMaxT + t) * XS;
+#pragma unroll
+                for (int a = 0; a < D; ++a) g[a * 32 + lane] = x[a];
+                g[D * 32 + lane] = mval;
+                u = fmaxf(u, mval);
+            }
+            if (PRUNE) {
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+                    }
+                    if (lane == 0) { sbox[b * 2 * D + a] = lo[a]; sbox[b * 2 * D + D + a] = hi[a]; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+                if (lane == 0) ub[b] = __float_as_uint(u);
+            }
+        }
+        if (tid < nb) cursor[tid] = 0;
+        __syncthreads();
+        float U = INFINITY;   // CTA-wide: the largest running minimum of any sample of the CTA
+        if (PRUNE) {
+            if (tid <= 2 * D) {
+                float v;
+                if (tid < D) { v = INFINITY; for (int b = 0; b < nb; ++b) v = fminf(v, sbox[b * 2 * D + tid]); }
+                else if (tid < 2 * D) { v = -INFINITY; for (int b = 0; b < nb; ++b) v = fmaxf(v, sbox[b * 2 * D + tid]); }
+                else { v = 0.f; for (int b = 0; b < nb; ++b) v = fmaxf(v, __uint_as_float(ub[b])); }
+                s_cbox[tid] = v;
+            }
+            __syncthreads();
+            U = s_cbox[2 * D];
+        }
+
+        // ---- gather / sweep ---------------------------------------------------------------------
+        int fill = 0;
+        for (;;) {
+            fill = st.template fill_tile<PRUNE>(fill, U);
             if (fill > 0) {
-                sweep(fill);
+                const int n = fill;
+                if (!PRUNE) {
+                    const int npad = (n + kUnroll - 1) / kUnroll * kUnroll;
+                    if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
+                    __syncthreads();
+                }
+                const int seg_len = P.seg;
+                const int nseg = (n + seg_len - 1) / seg_len;
+                int b = warp % nb;
+                bool have = false;     // registers hold brick b
+                int cnt = 0, nt = 0;   // survivors waiting in wbuf; groups of brick b
+                unsigned long long swept = 0;   // records swept for brick b in this stint
+                float x[kMaxT][D], m[kMaxT], blo[D], bhi[D], u = 0.f;
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) m[t] = 0.f;
+                auto bound = [&]() {
+                    float v = m[0];
+#pragma unroll
+                    for (int t = 1; t < kMaxT; ++t) v = fmaxf(v, m[t]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    return v;
+                };
+                for (;;) {
+                    int seg = 0;
+                    if (lane == 0) seg = atomicAdd(&cursor[b], 1);
+                    seg = __shfl_sync(0xffffffffu, seg, 0);
+                    if (seg >= nseg) {
+                        if (have) {
+                            // end of the stint on brick b: flush the survivors, merge the minima
+                            if (PRUNE && cnt > 0) {
+                                const int npad = (cnt + kUnroll - 1) / kUnroll * kUnroll;
+                                if (lane < npad - cnt) wbuf[cnt + lane] = rec_sentinel<D>();
+                                __syncwarp();
+                                sweep_records<D>(wbuf, npad, nt, x, m);
+                                __syncwarp();
+                                swept += (unsigned)cnt;
+                                cnt = 0;
+                            }
+#pragma unroll
+                            for (int t = 0; t < kMaxT; ++t)
+                                if (t < nt)
+                                    atomicMin(reinterpret_cast<unsigned *>(bricks + ((size_t)b * kMaxT + t) * XS + D * 32 + lane),
+                                              __float_as_uint(m[t]));
+                            if (PRUNE) {
+                                const float v = bound();
+                                if (lane == 0) atomicMin(&ub[b], __float_as_uint(v));
+                            }
+                            executed_evals += swept * (unsigned long long)(nt * 32);
+                            swept = 0;
+                            have = false;
+                        }
+                        // steal from the brick with the most unclaimed segments
+                        int best = lane < nb ? nseg - cursor[lane] : 0, who = lane;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+                            if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+                        }
+                        if (best <= 0) break;
+                        b = who;
+                        continue;
+                    }
+                    if (!have) {
+                        int gf;
+                        brick_span(blk_groups, nb, b, gf, nt);
+#pragma unroll
+                        for (int t = 0; t < kMaxT; ++t) {
+                            const float *g = bricks + ((size_t)b * kMaxT + t) * XS;
+#pragma unroll
+                            for (int a = 0; a < D; ++a) x[t][a] = g[a * 32 + lane];
+                            m[t] = g[D * 32 + lane];
+                        }
+                        if (PRUNE) {
+#pragma unroll
+                            for (int a = 0; a < D; ++a) { blo[a] = sbox[b * 2 * D + a]; bhi[a] = sbox[b * 2 * D + D + a]; }
+                            u = bound();
+                        }
+                        have = true;
+                    }
+                    const int lo = seg * seg_len, hi = min(n, lo + seg_len);
+                    if (!PRUNE) {
+                        sweep_records<D>(tile + lo, (hi - lo + kUnroll - 1) / kUnroll * kUnroll, nt, x, m);
+                        swept += (unsigned)(hi - lo);
+                    }
+                    for (int base = lo; PRUNE && base < hi; base += 32) {
+                        const int idx = base + lane;
+                        const RecT rec = tile[idx < hi ? idx : tile_cap];
+                        float own[D];
+                        rec_unpack<D>(rec, own);
+                        float box2 = 0.f;
+#pragma unroll
+                        for (int a = 0; a < D; ++a) {
+                            const float e = fmaxf(fmaxf(blo[a] - own[a], own[a] - bhi[a]), 0.f);
+                            box2 = fmaf(e, e, box2);
+                        }
+                        // 0.9999: the box distance and the pair distances are rounded differently
+                        const bool keep = idx < hi && box2 * 0.9999f <= u;
+                        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                        if (mask == 0u) continue;
+                        if (keep) wbuf[cnt + __popc(mask & lt_mask)] = rec;
+                        cnt += __popc(mask);
+                        if (cnt >= kSurvivorFlush) {
+                            __syncwarp();
+                            sweep_records<D>(wbuf, kSurvivorFlush, nt, x, m);
+                            swept += kSurvivorFlush;
+                            cnt -= kSurvivorFlush;
+                            RecT carry_rec;
+                            if (lane < cnt) carry_rec = wbuf[kSurvivorFlush + lane];
+                            __syncwarp();
+                            if (lane < cnt) wbuf[lane] = carry_rec;
+                            u = bound();
+                        }
+                    }
+                }
+                // ---- closing: every stint merged, tile free ------------------------------------
+                __syncthreads();
+                if (tid < nb) cursor[tid] = 0;
+                if (tid == 0) s_fill = 0;
+                if (PRUNE && warp == 0) {
+                    float v = lane < nb ? __uint_as_float(ub[lane]) : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (lane == 0) s_cbox[2 * D] = v;
+                }
+                __syncthreads();
+                if (PRUNE) U = s_cbox[2 * D];
                 fill = 0;
             }
-            if (stream_done) break;
+            if (st.done) break;
         }
 
         // ---- merge -----------------------------------------------------------------------------
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-            const long long r = (long long)(g0 + t) * 32 + lane;
-            if (t < nt && r < P.R && m[t] < INFINITY)
-                atomicMin(reinterpret_cast<unsigned *>(P.out + s * P.R + r), __float_as_uint(m[t]));
+        for (int b = warp; b < nb; b += W) {
+            int gf, gc;
+            brick_span(blk_groups, nb, b, gf, gc);
+            for (int t = 0; t < gc; ++t) {
+                const long long r = (long long)(blk_g0 + gf + t) * 32 + lane;
+                const float v = bricks[((size_t)b * kMaxT + t) * XS + D * 32 + lane];
+                if (r < P.R && v < INFINITY)
+                    atomicMin(reinterpret_cast<unsigned *>(P.out + s * P.R + r), __float_as_uint(v));
+            }
         }
-        if (lane == 0 && sb == 0 && inball > 0 && P.count_work) {
+        if (lane == 0 && sb == 0 && st.inball > 0 && P.count_work) {
             if (P.cand_count) atomicAdd(reinterpret_cast<unsigned long long *>(P.cand_count + s),
-                                        (unsigned long long)inball);
-            if (P.evals) atomicAdd(P.evals, (unsigned long long)inball * (unsigned long long)P.R);
+                                        (unsigned long long)st.inball);
+            if (P.evals) atomicAdd(P.evals, (unsigned long long)st.inball * (unsigned long long)P.R);
         }
-        executed_evals += executed * (unsigned long long)(nt * 32);
     }
     if (lane == 0 && executed_evals) atomicAdd(P.executed, executed_evals);
 }
 
-// launch with a given kernel shape
-template <int D, bool PRUNE, int MAXT, int MAXW, int MINB>
-int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
+// launch (seed pass + full pass in pruned mode)
+template <int D, bool PRUNE, int MAXW, int MINB>
+int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     using RecT = typename Rec<D>::type;
-    auto kern = cover_eval_kernel<D, PRUNE, MAXT, MAXW, MINB>;
-    const EvalShape sh = eval_shape(R, MAXT, MAXW);
+    auto kern = cover_eval_kernel<D, PRUNE, MAXW, MINB>;
     P.nsb = sh.nsb;
+    P.nb = sh.nb;
     P.groups = sh.groups;
     P.groups_per_block = sh.groups_per_block;
     const int NT = sh.W * 32;
-    // tile capacity: what the shared memory of an SM allows for MINB resident CTAs (narrow CTAs
-    // of small sample sets pack more per SM and get proportionally smaller tiles)
-    P.async_gather = get_option("async_gather", 1) != 0;
-    const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * kAsyncLPL * sizeof(RecT) : 0;
-    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + (size_t)(2 * NT + 1) * sizeof(int) + staging + 2048;
-    int per_sm_target = (MAXW * MINB * 32) / NT;
-    if (per_sm_target < 1) per_sm_target = 1;
-    if (per_sm_target > 20) per_sm_target = 20;
-    long long cap = ((long long)(227 * 1024) / per_sm_target - (long long)fixed) / (long long)sizeof(RecT);
+    // cp.async staging pays (marginally) for the 16-byte records of D <= 4; the 32-byte records of
+    // D >= 5 leave room for one record per lane and buffer only, where plain loads are faster
+    P.async_gather = get_option("async_gather", D <= 4 ? 1 : 0) != 0;
+    // sweep task = one brick x P.seg tile records; the exhaustive sweep has uniform tasks and
+    // prefers long ones (fewer loop prologues), the pruned sweep short ones (balance)
+    P.seg = get_option("seg", PRUNE ? 256 : 1024);
+    if (P.seg < 32) P.seg = 32;
+    P.seg = P.seg / kUnroll * kUnroll;
+    // dynamic shared memory: tile | staging rings | survivor buffers | bricks | boxes, bounds, cursors | runs
+    const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * async_lpl(D) * sizeof(RecT) : 0;
+    const size_t wbuf = PRUNE ? (size_t)sh.W * kSurvivorBuf * sizeof(RecT) : 0;
+    const size_t bricks = (size_t)sh.nb * brick_bytes(D);
+    const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
+    const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
+    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + staging + wbuf + bricks + misc + runs;
+    const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
+    long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
     if (cap > 4096) cap = 4096;
     const int forced_cap = get_option("tile_cap", 0);
-    if (forced_cap > 0) cap = forced_cap;
-    if (cap < 2 * NT) cap = 2 * NT;
+    if (forced_cap > 0 && forced_cap < cap) cap = forced_cap;
     cap = cap / kUnroll * kUnroll;
+    if (cap < 2 * NT)
+        return set_error(FLOOD_E_UNSUPPORTED, "cover_eval_kernel: shared memory budget exceeded (d=%d, %d bricks)", D, sh.nb);
     P.tile_cap = (int)cap;
-    const size_t smem = (size_t)(cap + kUnroll) * sizeof(RecT) + staging + (size_t)(2 * NT + 1) * sizeof(int);
+    size_t o = (size_t)(cap + kUnroll) * sizeof(RecT);
+    P.off_stage = (int)o;   o += staging;
+    P.off_wbuf = (int)o;    o += wbuf;
+    P.off_bricks = (int)o;  o += bricks;
+    P.off_misc = (int)o;    o += misc;
+    P.off_runs = (int)o;    o += runs;
+    const size_t smem = o;
     FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FLOOD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -803,15 +930,17 @@ int launch_eval_shape(CoverParams &P, int64_t R, cudaStream_t st) {
 template <int D>
 int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     const bool prune = get_option("prune", 1) != 0;
-    const int sh = pick_shape(prune);
-    if (!prune) {
-        if (sh == 1) return launch_eval_shape<D, false, 8, 4, 5>(P, R, st);
-        if (sh == 2) return launch_eval_shape<D, false, 8, 8, 2>(P, R, st);
-        return launch_eval_shape<D, false, 8, 20, 1>(P, R, st);
+    const EvalShape sh = eval_shape(R, D);
+    if (sh.minb == 1) {
+        if (prune) return launch_eval_shape<D, true, kWideWarps, 1>(P, sh, st);
+        return launch_eval_shape<D, false, kWideWarps, 1>(P, sh, st);
     }
-    if (sh == 1) return launch_eval_shape<D, true, 8, 4, 5>(P, R, st);
-    if (sh == 2) return launch_eval_shape<D, true, 8, 8, 2>(P, R, st);
-    return launch_eval_shape<D, true, 8, 20, 1>(P, R, st);
+    if (sh.minb == kMediumCtas) {
+        if (prune) return launch_eval_shape<D, true, kMediumWarps, kMediumCtas>(P, sh, st);
+        return launch_eval_shape<D, false, kMediumWarps, kMediumCtas>(P, sh, st);
+    }
+    if (prune) return launch_eval_shape<D, true, kNarrowWarps, kNarrowCtas>(P, sh, st);
+    return launch_eval_shape<D, false, kNarrowWarps, kNarrowCtas>(P, sh, st);
 }
 
 }  // namespace flood

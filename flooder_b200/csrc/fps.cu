@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(1024, 1) fps_grid_kernel(const FpsGridParams G
         key[j] = 0ull;
         if (c < gp.ncells && G.cell_start[c + 1] > G.cell_start[c]) {
             const int ix = (int)(c % gp.n[0]), iy = (int)((c / gp.n[0]) % gp.n[1]);
-            const int iz = (int)(c / ((long long)gp.n[0] * gp.n[1]));
+            // axes beyond the third are ignored here: the distance to the (x, y, z) footprint of a
+            // cell is still a lower bound of the distance to the cell
+            const int iz = (int)((c / ((long long)gp.n[0] * gp.n[1])) % gp.n[2]);
             cell_xyz[j] = ix | (iy << 10) | (iz << 20);
             key[j] = 0x7f800000ull << 32;   // +inf: every non-empty cell is live in iteration 0
         }
