@@ -94,5 +94,6 @@ EXPORTED_SYMBOLS = [
     "flood_bounding_balls_f32",
     "flood_covering_workspace_bytes", "flood_covering_radius_f32", "flood_covering_plan_f32",
     "flood_covering_bricks",
+    "flood_bounding_balls_f64", "flood_covering_workspace_bytes_f64", "flood_covering_radius_f64", "flood_face_max_f64",
     "flood_face_max_f32",
 ]

@@ -24,7 +24,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(OUT, "libflood_b200.so")
 EXT = os.path.join(OUT, "_flood_ext.so")
 
-CU_SOURCES = ["abi.cu", "cloud.cu", "balls.cu", "covering.cu", "fps.cu"] + [f"covering_d{d}.cu" for d in range(1, 9)]
+CU_SOURCES = ["abi.cu", "cloud.cu", "balls.cu", "covering.cu", "fps.cu", "f64.cu"] + [f"covering_d{d}.cu" for d in range(1, 9)]
 CU_HEADERS = ["common.cuh", "covering_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -80,17 +80,12 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_ext(force: bool = False, verbose: bool = False) -> str:
-    src = os.path.join(CSRC, "torch_binding.cpp")
-    if not (force or _stale(EXT, [src, os.path.join(INCLUDE, "flood_b200.h"), LIB])):
-        return EXT
+def _ext_command(cxx: str, src: str):
     import torch
     from torch.utils import cpp_extension
 
-    os.makedirs(OUT, exist_ok=True)
     incs = cpp_extension.include_paths("cuda") + [sysconfig.get_paths()["include"], INCLUDE]
     libdirs = cpp_extension.library_paths("cuda")
-    cxx = os.environ.get("CXX", "g++")
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_flood_ext",
            "-DTORCH_API_INCLUDE_EXTENSION_H",
            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
@@ -101,10 +96,50 @@ def build_ext(force: bool = False, verbose: bool = False) -> str:
         cmd += [f"-L{d}"]
     cmd += [f"-L{OUT}", "-lflood_b200", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
             "-ltorch_python", "-Wl,-rpath,$ORIGIN"]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
-    return EXT
+    return cmd
+
+
+_SELF_TEST = """
+import importlib.machinery, importlib.util, sys
+import torch
+loader = importlib.machinery.ExtensionFileLoader("_flood_ext", sys.argv[1])
+mod = importlib.util.module_from_spec(importlib.util.spec_from_loader("_flood_ext", loader, origin=sys.argv[1]))
+loader.exec_module(mod)
+try:
+    mod._raise_for_code(-4)
+except RuntimeError as exc:
+    assert "self-test failed (-4)" in str(exc)
+    print("ok")
+"""
+
+
+def _ext_self_test() -> bool:
+    """A library error code must surface as a Python RuntimeError.  (A toolchain whose start files /
+    libgcc differ from the system's has produced an extension that crashed on that path: the build
+    tries the next compiler instead of shipping it.)"""
+    res = subprocess.run([sys.executable, "-c", _SELF_TEST, EXT], capture_output=True, text=True)
+    return res.returncode == 0 and "ok" in res.stdout
+
+
+def build_ext(force: bool = False, verbose: bool = False) -> str:
+    src = os.path.join(CSRC, "torch_binding.cpp")
+    if not (force or _stale(EXT, [src, os.path.join(INCLUDE, "flood_b200.h"), LIB])):
+        return EXT
+    os.makedirs(OUT, exist_ok=True)
+    candidates = []
+    for cxx in (os.environ.get("FLOOD_CXX"), "/usr/bin/g++", shutil.which("g++"), os.environ.get("CXX")):
+        if cxx and os.path.exists(cxx) and cxx not in candidates:
+            candidates.append(cxx)
+    for cxx in candidates:
+        cmd = _ext_command(cxx, src)
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        if _ext_self_test():
+            return EXT
+        print(f"flooder_b200.build: extension built with {cxx} fails its error-path self-test, trying the next compiler",
+              file=sys.stderr)
+    raise RuntimeError("no host compiler produced a working _flood_ext.so")
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:

@@ -121,8 +121,13 @@ def _grid_weights_cached(n: int, dim: int, device_str: str) -> torch.Tensor:
     return weights
 
 
-def _grid_weights(n: int, dim: int, device) -> torch.Tensor:
+def _grid_weights(n: int, dim: int, device, dtype=torch.float32) -> torch.Tensor:
     """The weights of ``generate_grid`` only (cached per device; treated as read-only)."""
+    if dtype is torch.float64:
+        counts = torch.as_tensor(_lattice(int(n), int(dim)))
+        weights = torch.empty(counts.shape, dtype=torch.float64)
+        torch.divide(counts, n - 1, out=weights)
+        return weights.to(device)
     return _grid_weights_cached(int(n), int(dim), str(device))
 
 
@@ -332,19 +337,50 @@ def covering_cost(cloud: PreparedCloud, simplex_vertices: torch.Tensor) -> torch
     return ext.covering_plan(cloud.workspace, cloud.n, cloud.d, centers, radii).to(torch.float32)
 
 
+def covering_values_f64(cloud: PreparedCloud, points64: torch.Tensor, simplex_vertices: torch.Tensor,
+                        weights: torch.Tensor, grid_mode: bool, stats: Optional[dict] = None) -> torch.Tensor:
+    """float64 variant of ``covering_values`` (the reference evaluates float64 inputs in float64,
+    ``flooder/triton_kernels.py:226-229``): bounding balls, ball predicate, sample points and
+    distances in float64 on ``points64``; ``cloud`` (the float32-rounded prepared cloud) only
+    enumerates candidates.  Plain kernels, no pruning (``csrc/f64.cu``)."""
+    ext = _native.ext()
+    verts = simplex_vertices.to(torch.float64).contiguous()
+    w = weights.to(torch.float64).contiguous()
+    S, K = verts.shape[0], verts.shape[1]
+    support = _support_masks(w) if grid_mode else None
+    centers, radii = ext.bounding_balls_f64(verts)
+    rows = _slab_rows(S, 2 * w.shape[0], verts.device)
+    parts = []
+    for lo in range(0, S, rows):
+        hi = min(S, lo + rows)
+        min_d2, _counts, evals = ext.covering_radius_f64(cloud.workspace, points64, verts[lo:hi].contiguous(), w,
+                                                         centers[lo:hi].contiguous(), radii[lo:hi].contiguous())
+        parts.append(ext.face_max_f64(min_d2, support, K))
+        del min_d2
+        if stats is not None:
+            stats["evals"] = evals if lo == 0 else stats["evals"] + evals
+            stats["executed"] = stats["evals"]
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+
 def device_pass(cloud: PreparedCloud, simplex_vertices: torch.Tensor, weights: torch.Tensor, grid_mode: bool,
-                shard: Optional["fdist.Shard"] = None, stats: Optional[dict] = None) -> torch.Tensor:
+                shard: Optional["fdist.Shard"] = None, stats: Optional[dict] = None,
+                points64: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Everything ``flood_complex`` enqueues on the device for one dimension pass, given the
     prepared cloud: [cost plan + partition over ranks] -> bounding balls -> covering-radius kernel
     -> face maxima -> [all-gather of the per-simplex values].  Asynchronous; returns the device
     tensor of values for all simplices.  ``bench.py`` times exactly this function (plus the cloud
     build), so the benchmarked path cannot drift from the product path."""
+    if points64 is not None:
+        def compute(v):
+            return covering_values_f64(cloud, points64, v, weights, grid_mode, stats=stats)
+    else:
+        def compute(v):
+            return covering_values(cloud, v, weights, grid_mode=grid_mode, stats=stats)
     if shard is None:
-        return covering_values(cloud, simplex_vertices, weights, grid_mode=grid_mode, stats=stats)
-    return fdist.sharded_covering_values(
-        shard, simplex_vertices,
-        lambda v: covering_values(cloud, v, weights, grid_mode=grid_mode, stats=stats),
-        cost=covering_cost(cloud, simplex_vertices))
+        return compute(simplex_vertices)
+    return fdist.sharded_covering_values(shard, simplex_vertices, compute,
+                                         cost=covering_cost(cloud, simplex_vertices))
 
 
 def _scatter_face_values(table: FaceTable, cell_values: np.ndarray, values: Dict[int, np.ndarray]) -> None:
@@ -414,7 +450,7 @@ def flood_complex(
         raise TypeError(f"dtype ({dtype}) not supported")
     if dtype is torch.float64:
         warnings.warn(
-            "float64 inputs are evaluated in float32 by the sm_100a kernels",
+            "Using float64 kernels is slow on B200 (plain FP64 kernels, no pruning)",
             RuntimeWarning,
             stacklevel=2,
         )
@@ -424,6 +460,9 @@ def flood_complex(
     shard = fdist.current_shard()
     del landmarks_arg
     lms32 = landmarks.detach().to(torch.float32)
+    # float64 inputs are evaluated in float64 (as the reference does): original coordinates
+    points64 = points.detach().contiguous() if dtype is torch.float64 else None
+    lms64 = landmarks.detach().contiguous() if dtype is torch.float64 else None
     with _Stage("delaunay"):
         # host, as in the reference; triangulated in the precision the landmarks were given in
         cells, gudhi_tree = delaunay_complex(landmarks.detach().cpu().numpy())
@@ -441,15 +480,17 @@ def flood_complex(
 
     def launch(d_simplices_np: np.ndarray, weights: torch.Tensor) -> torch.Tensor:
         """Enqueue one dimension pass (asynchronous); returns the device tensor of values."""
-        simplex_vertices = lms32[torch.as_tensor(d_simplices_np, device=device)]
-        return device_pass(cloud, simplex_vertices, weights, grid_mode, shard)
+        index = torch.as_tensor(d_simplices_np, device=device)
+        if points64 is not None:
+            return device_pass(cloud, lms64[index], weights, grid_mode, shard, points64=points64)
+        return device_pass(cloud, lms32[index], weights, grid_mode, shard)
 
     # Grid mode on full-dimensional cells needs nothing but the cells: enqueue the kernels first
     # and build the face table on the host while the GPU works.
     pending = None
     if grid_mode and max_dimension == K - 1 and cells.shape[0] > 0:
         with _Stage("kernels"):
-            pending = launch(cells, _grid_weights(points_per_edge, max_dimension, device))
+            pending = launch(cells, _grid_weights(points_per_edge, max_dimension, device, dtype))
     with _Stage("face_table"):
         table = FaceTable(cells, n_vertices=lms32.shape[0])
         values = table.nan_values()       # NaN = not assigned (simplices above max_dimension)
@@ -468,10 +509,10 @@ def flood_complex(
                 continue
             if grid_mode:
                 sub = FaceTable(d_cells, n_vertices=table.base)
-                host_values = launch(d_cells, _grid_weights(points_per_edge, max_dimension, device)).cpu().numpy()
+                host_values = launch(d_cells, _grid_weights(points_per_edge, max_dimension, device, dtype)).cpu().numpy()
                 _scatter_face_values(sub, host_values, values)
             else:
-                weights = generate_uniform_weights(num_rand, d, device, torch.float32)
+                weights = generate_uniform_weights(num_rand, d, device, dtype)
                 if shard is not None:
                     # the weights come from each process's own CPU generator (core.py:423-425 of the
                     # reference): rank 0's draw is used everywhere so that a value does not depend

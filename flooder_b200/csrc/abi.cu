@@ -98,6 +98,26 @@ int flood_device_info(int *sm_count, int *sm_clock_khz) {
     return FLOOD_OK;
 }
 
+int flood_bounding_balls_f64(const double *verts, int64_t S, int K, int d, double *centers, double *radii,
+                             void *stream) {
+    return bounding_balls_f64(verts, S, K, d, centers, radii, (cudaStream_t)stream);
+}
+
+size_t flood_covering_workspace_bytes_f64(int64_t S, int d) { return covering_workspace_bytes_f64(S, d); }
+
+int flood_covering_radius_f64(const void *cloud_workspace, const double *pts, int64_t n, int d, const double *verts,
+                              int64_t S, int K, const double *weights, int64_t R, const double *centers,
+                              const double *radii, double *out_min_dist2, int64_t *out_cand_count,
+                              unsigned long long *out_evals, void *workspace, size_t workspace_bytes, void *stream) {
+    return covering_radius_f64(cloud_workspace, pts, n, d, verts, S, K, weights, R, centers, radii, out_min_dist2,
+                               out_cand_count, out_evals, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int flood_face_max_f64(const double *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, double *out,
+                       void *stream) {
+    return face_max_f64(min_dist2, S, R, support, K, out, (cudaStream_t)stream);
+}
+
 int flood_set_option(const char *name, int value) {
     if (!name) return 0;
     std::lock_guard<std::mutex> lock(g_opt_mutex);

@@ -52,8 +52,9 @@ __global__ void bbox_kernel(const float *__restrict__ pts, int64_t n, int d, uns
 
 // Choose a cubic cell edge h so that the box holds ~ n / points_per_cell cells.
 __global__ void grid_params_kernel(const unsigned *bbox, int64_t n, int d, int points_per_cell,
-                                   int64_t max_cells, GridParams *gp) {
-    const int g = grid_axes(d);
+                                   int64_t max_cells, int axes_limit, GridParams *gp) {
+    int g = grid_axes(d);
+    if (axes_limit > 0 && axes_limit < g) g = axes_limit;
     float lo[GA], ext[GA];
     double vol = 1.0;
     int live = 0;
@@ -210,7 +211,7 @@ int cloud_build(const float *pts, int64_t n, int d, int points_per_cell, void *w
 
     bbox_init_kernel<<<1, 32, 0, st>>>(bbox);
     bbox_kernel<<<blocks, threads, 0, st>>>(pts, n, d, bbox);
-    grid_params_kernel<<<1, 1, 0, st>>>(bbox, n, d, points_per_cell, L.max_cells, gp);
+    grid_params_kernel<<<1, 1, 0, st>>>(bbox, n, d, points_per_cell, L.max_cells, get_option("grid_axes", 0), gp);
     FLOOD_CUDA_CHECK(cudaMemsetAsync(cell_fill, 0, (size_t)L.max_cells * 4, st));
     cell_count_kernel<<<blocks, threads, 0, st>>>(pts, n, d, gp, cell_id, cell_fill);
     cell_scan_kernel<<<1, 1024, 0, st>>>(gp, cell_fill, cell_start);

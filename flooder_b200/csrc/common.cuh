@@ -197,6 +197,15 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
 int covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block);
 int covering_plan(const void *cloud_ws, int64_t n, int d, const float *centers, const float *radii,
                   int64_t S, int32_t *out_tested, cudaStream_t st);
+int bounding_balls_f64(const double *verts, int64_t S, int K, int d, double *centers, double *radii,
+                       cudaStream_t st);
+size_t covering_workspace_bytes_f64(int64_t S, int d);
+int covering_radius_f64(const void *cloud_ws, const double *pts, int64_t n, int d, const double *verts, int64_t S,
+                        int K, const double *weights, int64_t R, const double *centers, const double *radii,
+                        double *out_min_dist2, int64_t *out_cand_count, unsigned long long *out_evals, void *ws,
+                        size_t ws_bytes, cudaStream_t st);
+int face_max_f64(const double *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, double *out,
+                 cudaStream_t st);
 int face_max(const float *min_dist2, int64_t S, int64_t R, const int32_t *support, int K, float *out,
              cudaStream_t st);
 size_t fps_workspace_bytes(int64_t n, int d, int64_t n_lms);

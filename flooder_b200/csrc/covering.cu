@@ -195,6 +195,27 @@ int covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *br
     return total;
 }
 
+// work items of a call: tested[s], the scanned chunk counts item_base[], a cleared queue (shared by
+// the float32 kernel's caller below and the float64 path in f64.cu)
+int covering_plan_items(CoverParams &P, int d, int64_t S, void *ws, cudaStream_t st) {
+    const CoverLayout L = cover_layout(S);
+    char *wbase = static_cast<char *>(ws);
+    P.tested = reinterpret_cast<int *>(wbase + L.off_tested);
+    P.item_base = reinterpret_cast<long long *>(wbase + L.off_item_base);
+    P.item_base_seed = nullptr;
+    P.queue = reinterpret_cast<unsigned long long *>(wbase + L.off_queue);
+    P.executed = P.queue + 2;
+    P.chunk = get_option("chunk", 8192);
+    if (P.chunk < 256) P.chunk = 256;
+    P.rows_per_chunk_factor = get_option("rows_per_chunk_factor", 32);
+    FLOOD_CUDA_CHECK(cudaMemsetAsync(P.queue, 0, 64, st));
+    launch_plan(P, d, S, st);
+    cover_scan_kernel<<<1, 1024, 0, st>>>(P.item_base, S);
+    count_launches(2);
+    FLOOD_LAUNCH_CHECK("cover plan kernels");
+    return FLOOD_OK;
+}
+
 size_t covering_workspace_bytes(int64_t S, int64_t R, int d) {
     (void)R; (void)d;
     return (size_t)cover_layout(S < 1 ? 1 : S).total;

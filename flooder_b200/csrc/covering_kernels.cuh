@@ -76,10 +76,11 @@ __device__ __forceinline__ BallCells<G> ball_cells(const float *c, float r, cons
     b.nrows = 1;
 #pragma unroll
     for (int a = 0; a < G; ++a) {
-        b.g[a] = cell_coord(c[a], gp.origin[a], gp.inv_h);
+        // an axis the grid does not bin (gp.g < G: option "grid_axes") is one cell holding the centre
+        b.g[a] = a < gp.g ? cell_coord(c[a], gp.origin[a], gp.inv_h) : 0.5f;
         if (a > 0) {
-            const int lo = max(0, clamp_cell(b.g[a] - gr, gp.n[a]));
-            const int hi = min(gp.n[a] - 1, clamp_cell(b.g[a] + gr, gp.n[a]));
+            const int lo = a < gp.g ? max(0, clamp_cell(b.g[a] - gr, gp.n[a])) : 0;
+            const int hi = a < gp.g ? min(gp.n[a] - 1, clamp_cell(b.g[a] + gr, gp.n[a])) : 0;
             b.i0[a] = lo;
             b.nb[a] = max(0, hi - lo + 1);
             b.nrows *= b.nb[a];
@@ -867,8 +868,6 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     // sweep task = one brick x P.seg tile records; the exhaustive sweep has uniform tasks and
     // prefers long ones (fewer loop prologues), the pruned sweep short ones (balance)
     P.seg = get_option("seg", PRUNE ? 256 : 1024);
-    if (P.seg < 32) P.seg = 32;
-    P.seg = P.seg / kUnroll * kUnroll;
     // dynamic shared memory: tile | staging rings | survivor buffers | bricks | boxes, bounds, cursors | runs
     const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * async_lpl(D) * sizeof(RecT) : 0;
     const size_t wbuf = PRUNE ? (size_t)sh.W * kSurvivorBuf * sizeof(RecT) : 0;
@@ -879,12 +878,19 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
     long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
     if (cap > 4096) cap = 4096;
-    const int forced_cap = get_option("tile_cap", 0);
-    if (forced_cap > 0 && forced_cap < cap) cap = forced_cap;
+    const int forced_cap = get_option("tile_cap", 0);   // experiments: a smaller tile (at least 2 records per thread)
+    if (forced_cap > 0 && forced_cap < cap) cap = forced_cap > 2 * NT ? forced_cap : (cap < 2 * NT ? cap : 2 * NT);
     cap = cap / kUnroll * kUnroll;
     if (cap < 2 * NT)
         return set_error(FLOOD_E_UNSUPPORTED, "cover_eval_kernel: shared memory budget exceeded (d=%d, %d bricks)", D, sh.nb);
     P.tile_cap = (int)cap;
+    {
+        // at least ~4 tasks per warp and tile, also when a few bricks are shared by all warps
+        const long long balanced = (cap * sh.nb / (4 * sh.W) + 31) / 32 * 32;
+        if (get_option("seg", 0) <= 0 && P.seg > balanced) P.seg = (int)balanced;
+        if (P.seg < 32) P.seg = 32;
+        P.seg = P.seg / kUnroll * kUnroll;
+    }
     size_t o = (size_t)(cap + kUnroll) * sizeof(RecT);
     P.off_stage = (int)o;   o += staging;
     P.off_wbuf = (int)o;    o += wbuf;

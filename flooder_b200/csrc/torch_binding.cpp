@@ -174,6 +174,76 @@ torch::Tensor face_max(const torch::Tensor &min_dist2, const c10::optional<torch
     return out;
 }
 
+// ---- float64 path -------------------------------------------------------------------------
+void need_cuda_f64(const torch::Tensor &t, const char *name) {
+    TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor (flooder_b200 has no CPU path)");
+    TORCH_CHECK(t.scalar_type() == torch::kFloat64, name, " must be float64");
+    TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+
+std::tuple<torch::Tensor, torch::Tensor> bounding_balls_f64(const torch::Tensor &verts) {
+    need_cuda_f64(verts, "simplex_vertices");
+    TORCH_CHECK(verts.dim() == 3, "simplex_vertices must be (S, K, D)");
+    const c10::cuda::CUDAGuard guard(verts.device());
+    const int64_t S = verts.size(0);
+    auto centers = torch::empty({S, verts.size(2)}, verts.options());
+    auto radii = torch::empty({S}, verts.options());
+    check(flood_bounding_balls_f64(verts.data_ptr<double>(), S, (int)verts.size(1), (int)verts.size(2),
+                                   centers.data_ptr<double>(), radii.data_ptr<double>(), current_stream(verts)),
+          "flood_bounding_balls_f64");
+    return {centers, radii};
+}
+
+// returns (min_dist2 [S,R] float64, cand_count [S] int64, evals [1] int64)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> covering_radius_f64(
+    const torch::Tensor &cloud_ws, const torch::Tensor &pts, const torch::Tensor &verts, const torch::Tensor &weights,
+    const torch::Tensor &centers, const torch::Tensor &radii) {
+    need_cuda_f64(pts, "points");
+    need_cuda_f64(verts, "simplex_vertices");
+    need_cuda_f64(weights, "weights");
+    need_cuda_f64(centers, "centers");
+    need_cuda_f64(radii, "radii");
+    TORCH_CHECK(cloud_ws.is_cuda() && cloud_ws.scalar_type() == torch::kUInt8, "cloud workspace must be CUDA uint8");
+    TORCH_CHECK(pts.dim() == 2 && verts.dim() == 3 && verts.size(2) == pts.size(1), "bad point / vertex shapes");
+    TORCH_CHECK(weights.dim() == 2 && weights.size(1) == verts.size(1), "weights must be (R, K)");
+    const int64_t n = pts.size(0), d = pts.size(1), S = verts.size(0), K = verts.size(1), R = weights.size(0);
+    TORCH_CHECK(centers.dim() == 2 && centers.size(0) == S && centers.size(1) == d && radii.numel() == S, "bad ball shapes");
+    const c10::cuda::CUDAGuard guard(verts.device());
+    auto out = torch::empty({S, R}, verts.options());
+    auto counts = torch::empty({S}, verts.options().dtype(torch::kInt64));
+    auto evals = torch::zeros({1}, verts.options().dtype(torch::kInt64));
+    const size_t wsb = flood_covering_workspace_bytes_f64(S, (int)d);
+    auto ws = bytes_like(verts, wsb);
+    check(flood_covering_radius_f64(cloud_ws.data_ptr(), pts.data_ptr<double>(), n, (int)d, verts.data_ptr<double>(), S,
+                                    (int)K, weights.data_ptr<double>(), R, centers.data_ptr<double>(),
+                                    radii.data_ptr<double>(), out.data_ptr<double>(), counts.data_ptr<int64_t>(),
+                                    reinterpret_cast<unsigned long long *>(evals.data_ptr<int64_t>()), ws.data_ptr(), wsb,
+                                    current_stream(verts)),
+          "flood_covering_radius_f64");
+    return {out, counts, evals};
+}
+
+torch::Tensor face_max_f64(const torch::Tensor &min_dist2, const c10::optional<torch::Tensor> &support, int64_t K) {
+    need_cuda_f64(min_dist2, "min_dist2");
+    TORCH_CHECK(min_dist2.dim() == 2, "min_dist2 must be (S, R)");
+    const int64_t S = min_dist2.size(0), R = min_dist2.size(1);
+    const int32_t *sup = nullptr;
+    int64_t width = 1;
+    if (support.has_value()) {
+        TORCH_CHECK(support->is_cuda() && support->scalar_type() == torch::kInt32 && support->is_contiguous() &&
+                        support->numel() == R,
+                    "support must be a contiguous CUDA int32 tensor of R masks");
+        sup = support->data_ptr<int32_t>();
+        width = (int64_t(1) << K) - 1;
+    }
+    const c10::cuda::CUDAGuard guard(min_dist2.device());
+    auto out = torch::empty({S, width}, min_dist2.options());
+    check(flood_face_max_f64(min_dist2.data_ptr<double>(), S, R, sup, (int)K, out.data_ptr<double>(),
+                             current_stream(min_dist2)),
+          "flood_face_max_f64");
+    return out;
+}
+
 std::tuple<double, int64_t> kernel_ms(const std::string &name, bool reset) {
     double ms = 0.0;
     long launches = 0;
@@ -196,7 +266,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("face_max", &face_max);
     m.def("covering_plan", &covering_plan);
     m.def("covering_bricks", &covering_bricks);
+    m.def("bounding_balls_f64", &bounding_balls_f64);
+    m.def("covering_radius_f64", &covering_radius_f64);
+    m.def("face_max_f64", &face_max_f64);
     m.def("set_option", &set_option);
+    // error plumbing self-test: turns a library error code into the Python exception a failing call raises
+    m.def("_raise_for_code", [](int64_t rc) { check((int)rc, "self-test"); });
     m.def("launch_count", [](bool reset) { return (int64_t)flood_launch_count(reset ? 1 : 0); });
     m.def("kernel_ms", &kernel_ms);
 }

@@ -146,6 +146,25 @@ int flood_covering_plan_f32(const void *cloud_workspace, int64_t n, int d, const
 int flood_face_max_f32(const float *min_dist2, int64_t S, int64_t R, const int32_t *support,
                        int K, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * float64 variants (the reference runs its kernels in float64 for float64 inputs,
+ * flooder/triton_kernels.py:226-229, flooder/core.py:116-123).  Same meaning as the float32 entry
+ * points; the ball predicate, the sample points and the distances are evaluated in float64 on
+ * `pts` (the original coordinates, [n, d] row-major).  `cloud_workspace` is the prepared cloud of the
+ * SAME points rounded to float32 (flood_cloud_build_f32): it only enumerates candidates.  Plain
+ * kernels (no pruning): B200's FP64 rate is a fraction of its FP32 rate.
+ * ------------------------------------------------------------------------------------- */
+int flood_bounding_balls_f64(const double *verts, int64_t S, int K, int d, double *centers,
+                             double *radii, void *stream);
+size_t flood_covering_workspace_bytes_f64(int64_t S, int d);
+int flood_covering_radius_f64(const void *cloud_workspace, const double *pts, int64_t n, int d,
+                              const double *verts, int64_t S, int K, const double *weights, int64_t R,
+                              const double *centers, const double *radii, double *out_min_dist2,
+                              int64_t *out_cand_count, unsigned long long *out_evals, void *workspace,
+                              size_t workspace_bytes, void *stream);
+int flood_face_max_f64(const double *min_dist2, int64_t S, int64_t R, const int32_t *support, int K,
+                       double *out, void *stream);
+
 /* Tuning knobs for experiments (process-wide; returns the previous value, -1 if it was unset). */
 int flood_set_option(const char *name, int value);
 

@@ -303,3 +303,23 @@ def test_covering_bricks_query_without_gpu():
     assert sum(groups) == 1
     lib = _native.cdll()
     assert lib.flood_covering_bricks(0, 3, None, 0, None) == -1
+
+
+def test_library_error_codes_become_python_exceptions():
+    """An error code returned across the C ABI must reach Python as a RuntimeError carrying
+    flood_last_error() -- not crash the interpreter.  Run in a subprocess so that a crash is a test
+    failure instead of the end of the session."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from flooder_b200 import _native\n"
+            "ext = _native.ext()\n"
+            "ext._raise_for_code(0)\n"
+            "try:\n"
+            "    ext._raise_for_code(-4)\n"
+            "except RuntimeError as exc:\n"
+            "    assert 'failed (-4)' in str(exc)\n"
+            "    print('ok')\n") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0 and "ok" in res.stdout, (res.returncode, res.stderr[-500:])

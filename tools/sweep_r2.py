@@ -37,7 +37,6 @@ def main():
         _, radii = ext.bounding_balls(verts)
         verts = verts[torch.argsort(radii, descending=True)].contiguous()    # largest balls first, as core does
         w = core._grid_weights(ppe, d, "cuda")
-        pc = core.PreparedCloud(pts)
         peak = sms * 128 * 1.965e9 / SLOTS[d]
         ref = None
         print(f"[{name}] n={n} lms={n_lms} d={d} ppe={ppe} S={len(cells)} R={w.shape[0]}", flush=True)
@@ -47,6 +46,7 @@ def main():
             core.USE_BRICKS = bool(bricks)
             prev = {k: ext.set_option(k, int(v)) for k, v in opts.items()}
             try:
+                pc = core.PreparedCloud(pts)          # cloud options (points_per_cell, grid_axes) apply here
                 best = None
                 for rep in range(3):
                     ext.kernel_ms("cover_eval", True)
@@ -73,7 +73,7 @@ def main():
             finally:
                 for k, v in prev.items():
                     ext.set_option(k, v)
-        del pts, pc
+        del pts
 
 
 if __name__ == "__main__":
