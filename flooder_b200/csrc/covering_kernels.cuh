@@ -153,7 +153,7 @@ inline EvalShape eval_shape(int64_t R, int d) {
     const int bricks = (sh.groups + kMaxT - 1) / kMaxT;
     const int small_max = get_option("small_max_bricks", 2);
     if (bricks <= small_max) {
-        const bool narrow = get_option("small_shape", 0) == 1;
+        const bool narrow = get_option("small_shape", 1) == 1;   // measured: narrow beats medium in 5-D
         sh.W = narrow ? kNarrowWarps : kMediumWarps;
         sh.minb = narrow ? kNarrowCtas : kMediumCtas;
         sh.nb = bricks;
@@ -877,7 +877,8 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     const size_t fixed = (size_t)kUnroll * sizeof(RecT) + staging + wbuf + bricks + misc + runs;
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
     long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
-    if (cap > 4096) cap = 4096;
+    const int cap_max = get_option("tile_cap_max", 4096);
+    if (cap > cap_max) cap = cap_max;
     const int forced_cap = get_option("tile_cap", 0);   // experiments: a smaller tile (at least 2 records per thread)
     if (forced_cap > 0 && forced_cap < cap) cap = forced_cap > 2 * NT ? forced_cap : (cap < 2 * NT ? cap : 2 * NT);
     cap = cap / kUnroll * kUnroll;

@@ -20,8 +20,10 @@
  *     and the calls return without synchronising, except where stated;
  *   - return value 0 = success, negative = error (FLOOD_E_*); a human-readable message for
  *     the calling thread's last error is returned by flood_last_error();
- *   - no exceptions cross the boundary; the functions are re-entrant per (device, stream)
- *     as long as the workspaces are distinct.
+ *   - no exceptions cross the boundary; the compute entry points are re-entrant per (device,
+ *     stream) as long as the workspaces are distinct.  flood_set_option, flood_kernel_ms and
+ *     flood_launch_count are process-wide diagnostics (one option table, one set of timers) and
+ *     are not covered by that guarantee: set options before concurrent use, not during it.
  */
 #ifndef FLOOD_B200_H
 #define FLOOD_B200_H
@@ -71,9 +73,9 @@ int flood_fps_grid_f32(const void *cloud_workspace, const float *pts, int64_t n,
                        void *stream);
 
 /* ---------------------------------------------------------------------------------------
- * Cloud preparation: bins the cloud into a uniform cell grid over its first min(d,3) axes and
- * stores it cell-sorted as padded float4 records, so that a ball maps to a few contiguous
- * runs.  The prepared cloud lives entirely inside `workspace`; the same (pointer, n, d) triple
+ * Cloud preparation: bins the cloud into a uniform cell grid over its first min(d,5) axes and
+ * stores it cell-sorted as padded records (float2 / float4 / 2 x float4), so that a ball maps to
+ * a few contiguous runs.  The prepared cloud lives entirely inside `workspace`; the same (pointer, n, d) triple
  * is handed to flood_covering_radius_f32.  points_per_cell <= 0 selects the default.
  * ------------------------------------------------------------------------------------- */
 size_t flood_cloud_workspace_bytes(int64_t n, int d);
@@ -105,12 +107,13 @@ int flood_bounding_balls_f32(const float *verts, int64_t S, int K, int d, float 
  *   out_evals         host-invisible device counter (1 x uint64) or NULL: sum_s R * cand_count[s],
  *                     the algorithmic work count E of the call
  *
- * By default (option "prune" = 1) the sweep is pruned exactly: every warp skips the candidates
- * that are at least as far from the box of its sample points as its largest running minimum, after
- * a seed pass over every 16th stream position (option "seed_stride").  The result is bit-identical
- * to the exhaustive sweep ("prune" = 0); fewer evaluations are executed, E still counts the
- * reference's ball rule.  The number of evaluations actually executed is left as a uint64 at byte
- * FLOOD_COVER_WS_EXECUTED_OFFSET of `workspace` (device memory).
+ * By default (option "prune" = 1) the sweep is pruned exactly: the samples are handled in bricks
+ * of up to 256; a candidate at least as far from the bounding box of a brick as the brick's largest
+ * running minimum is skipped for that brick, after a seed pass over every 32nd record of the
+ * candidate stream (option "seed_stride") has given every sample a finite bound.  The result is
+ * bit-identical to the exhaustive sweep ("prune" = 0); fewer evaluations are executed, E still
+ * counts the reference's ball rule.  The number of evaluations actually executed is left as a
+ * uint64 at byte FLOOD_COVER_WS_EXECUTED_OFFSET of `workspace` (device memory).
  * ------------------------------------------------------------------------------------- */
 #define FLOOD_COVER_WS_EXECUTED_OFFSET 16
 size_t flood_covering_workspace_bytes(int64_t S, int64_t R, int d);

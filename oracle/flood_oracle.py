@@ -59,8 +59,10 @@ def generate_grid(n: int, dim: int, dtype=np.float32):
             verts_k.append(axes[~np.isin(axes, zero_set)])
         face_idxs.append(np.stack(rows_k))
         vertex_idxs.append(np.stack(verts_k))
-    # torch.divide(int64, python int, out=<dtype>) computes in the floating result type
-    weights = counts.astype(dtype) / dtype(n - 1)
+    # torch.divide(int64 tensor, python int, out=<dtype>) (core.py:400-401) divides in the promoted
+    # type of its inputs -- float32, torch's default -- and only then converts to the dtype of
+    # `out`: float64 weights of the reference carry float32-rounded quotients.
+    weights = counts.astype(np.float32) / np.float32(n - 1)
     return weights.astype(dtype), vertex_idxs, face_idxs
 
 

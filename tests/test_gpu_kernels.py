@@ -88,7 +88,7 @@ def test_fps_streaming_mode(ext):
 
 @pytest.mark.parametrize("mode", [0, 1])
 def test_fps_exchange_modes(ext, mode):
-    """Grid-wide argmax via cooperative-groups grid sync (0) or the counter barrier (1, default)."""
+    """Grid-wide argmax via cooperative-groups grid sync (0, the default) or the counter barrier (1)."""
     pts = _cloud("gauss", 40_000, 3, seed=4)
     want = native.fps(pts.numpy(), 150, 0)
     dev = pts.cuda()
