@@ -205,7 +205,7 @@ int covering_plan_items(CoverParams &P, int d, int64_t S, void *ws, cudaStream_t
     P.item_base_seed = nullptr;
     P.queue = reinterpret_cast<unsigned long long *>(wbase + L.off_queue);
     P.executed = P.queue + 2;
-    P.chunk = get_option("chunk", 8192);
+    P.chunk = get_option("chunk", 16384);
     if (P.chunk < 256) P.chunk = 256;
     P.rows_per_chunk_factor = get_option("rows_per_chunk_factor", 32);
     FLOOD_CUDA_CHECK(cudaMemsetAsync(P.queue, 0, 64, st));
@@ -262,7 +262,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
         const long long mult = get_option("seed_chunk_mult", 0) > 0 ? get_option("seed_chunk_mult", 0) : seed_stride;
         if (prune && seed_stride > 1 && mult > 1) {
             P.item_base_seed = reinterpret_cast<long long *>(wbase + L.off_item_base_seed);
-            long long cs = (long long)(get_option("chunk", 8192) < 256 ? 256 : get_option("chunk", 8192)) * mult;
+            long long cs = (long long)(get_option("chunk", 16384) < 256 ? 256 : get_option("chunk", 16384)) * mult;
             P.chunk_seed = (int)(cs > (1ll << 30) ? (1ll << 30) : cs);
         }
     }
@@ -272,7 +272,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
     P.R = R;
     P.K = K;
     P.nsb = 1;
-    P.chunk = get_option("chunk", 8192);
+    P.chunk = get_option("chunk", 16384);
     if (P.chunk < 256) P.chunk = 256;
     P.rows_per_chunk_factor = get_option("rows_per_chunk_factor", 32);
 

@@ -877,7 +877,7 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     const size_t fixed = (size_t)kUnroll * sizeof(RecT) + staging + wbuf + bricks + misc + runs;
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
     long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
-    const int cap_max = get_option("tile_cap_max", 4096);
+    const int cap_max = get_option("tile_cap_max", 8192);
     if (cap > cap_max) cap = cap_max;
     const int forced_cap = get_option("tile_cap", 0);   // experiments: a smaller tile (at least 2 records per thread)
     if (forced_cap > 0 && forced_cap < cap) cap = forced_cap > 2 * NT ? forced_cap : (cap < 2 * NT ? cap : 2 * NT);

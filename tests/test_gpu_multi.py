@@ -53,7 +53,9 @@ def _worker(rank, world, port, out_dir):
         np.random.seed(7 + rank)
         any_start = fb.flood_complex(pts, 80, points_per_edge=8, start_idx=None)
 
-        # a larger job: more simplices than ranks x warps, heavy-tailed costs
+        # a larger job: more simplices than ranks x warps, heavy-tailed costs (same cloud on every rank)
+        torch.manual_seed(43)
+        np.random.seed(43)
         big = fb.generate_noisy_torus_points_3d(300_000).cuda()
         big_sharded = fb.flood_complex(big, 400, points_per_edge=20)
         os.environ["FLOODER_B200_NO_SHARD"] = "1"
