@@ -267,3 +267,10 @@ def test_uniform_5d_2m_2k_sampled_two_sided(parity_record):
     largest lattice the reference can hold in 5-D)."""
     seed_all()
     _sampled_job("uniform5d_2m_2k_ppe6", torch.rand(2_000_000, 5), 2000, 6, 600, parity_record)
+
+
+def test_uniform_6d_2m_2k_sampled_two_sided(parity_record):
+    """BASELINE configs[4], the 6-D half: uniform 6-D cloud, 2 M points, 2 k landmarks, 4 points per
+    edge (R = 84).  The host Delaunay step (Qhull, ~1.4 M cells) dominates the test."""
+    seed_all()
+    _sampled_job("uniform6d_2m_2k_ppe4", torch.rand(2_000_000, 6), 2000, 4, 300, parity_record)
