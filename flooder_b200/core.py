@@ -257,11 +257,15 @@ def _slab_rows(S: int, R: int, device) -> int:
     """Simplices per kernel call such that the (rows, R) float32 ``min_dist2`` buffer stays within
     a quarter of the free device memory (at most 8 GiB).  The reference bounds the same buffer with
     ``batch_size`` (``flooder/core.py:193-226``); here one call normally takes every simplex."""
-    free, _total = torch.cuda.mem_get_info(device)
-    budget = min(free // 4, 8 << 30)
     override = os.environ.get("FLOODER_B200_SLAB_BYTES")
     if override:
         budget = int(override)
+    elif 4 * S * max(R, 1) <= (2 << 30):
+        return S            # small enough not to need a look at the free memory (cudaMemGetInfo stalls
+                            # the submitting thread for tens of milliseconds every few calls)
+    else:
+        free, _total = torch.cuda.mem_get_info(device)
+        budget = min(free // 4, 8 << 30)
     return max(1, min(S, int(budget // (4 * max(R, 1)))))
 
 

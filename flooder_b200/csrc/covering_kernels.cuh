@@ -10,8 +10,7 @@ namespace flood {
 constexpr int kUnroll = 4;       // candidates per inner-loop trip
 // cp.async gather: records per lane and staging buffer (one for the 32-byte records of D >= 5)
 __host__ __device__ constexpr int async_lpl(int d) { return d <= 4 ? 2 : 1; }
-constexpr int kSurvivorFlush = 64;   // pruned sweep: survivors collected per warp before they are swept
-constexpr int kSurvivorBuf = kSurvivorFlush + 32;
+constexpr int kSurvivorFlush = 32;   // pruned sweep: survivors collected per warp before they are swept (default)
 
 struct CoverParams {
     const GridParams *gp;
@@ -41,6 +40,8 @@ struct CoverParams {
     int groups_per_block;    // groups handled by one CTA pass (sample block)
     int nb;                  // bricks per sample block (shared-memory resident)
     int seg;                 // tile records per sweep task (work-stealing granularity)
+    int flush;               // pruned sweep: survivors collected per warp before they are swept (multiple of 4;
+                             // the per-warp buffer holds flush + 32 records)
     int tile_cap;            // candidate records per shared-memory tile
     // dynamic shared memory layout (byte offsets; tile at 0)
     int off_stage, off_wbuf, off_bricks, off_misc, off_runs;
@@ -522,7 +523,7 @@ __device__ __forceinline__ void sweep_records(const typename Rec<D>::type *recs,
 // PRUNE (default) skips work exactly: per task the warp tests the segment's records, 32 at a
 // time, against the bounding box of the brick's samples -- a record at least as far from the box
 // as the brick's largest running minimum u cannot lower any minimum -- and collects the survivors
-// in a per-warp buffer that is swept kSurvivorFlush records at a time.  u only shrinks, so a skip
+// in a per-warp buffer that is swept P.flush (32) records at a time.  u only shrinks, so a skip
 // stays justified; the minima are bit-identical to the exhaustive sweep
 // (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter candidate rule" of
 // the unit of work E is still counted by the reference's ball rule, fewer
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     const int nb = P.nb;
     const int tile_cap = P.tile_cap;
     RecT *tile = reinterpret_cast<RecT *>(smem_raw);
-    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * kSurvivorBuf;
+    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * (P.flush + 32);
     float *bricks = reinterpret_cast<float *>(smem_raw + P.off_bricks);       // [nb][kMaxT][D+1][32]
     float *sbox = reinterpret_cast<float *>(smem_raw + P.off_misc);           // [nb][2D]
     unsigned *ub = reinterpret_cast<unsigned *>(sbox + nb * 2 * D);           // [nb] largest minimum per brick
@@ -802,13 +803,13 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         if (mask == 0u) continue;
                         if (keep) wbuf[cnt + __popc(mask & lt_mask)] = rec;
                         cnt += __popc(mask);
-                        if (cnt >= kSurvivorFlush) {
+                        if (cnt >= P.flush) {
                             __syncwarp();
-                            sweep_records<D>(wbuf, kSurvivorFlush, nt, x, m);
-                            swept += kSurvivorFlush;
-                            cnt -= kSurvivorFlush;
+                            sweep_records<D>(wbuf, P.flush, nt, x, m);
+                            swept += (unsigned)P.flush;
+                            cnt -= P.flush;
                             RecT carry_rec;
-                            if (lane < cnt) carry_rec = wbuf[kSurvivorFlush + lane];
+                            if (lane < cnt) carry_rec = wbuf[P.flush + lane];
                             __syncwarp();
                             if (lane < cnt) wbuf[lane] = carry_rec;
                             u = bound();
@@ -870,7 +871,11 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     P.seg = get_option("seg", PRUNE ? 256 : 1024);
     // dynamic shared memory: tile | staging rings | survivor buffers | bricks | boxes, bounds, cursors | runs
     const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * async_lpl(D) * sizeof(RecT) : 0;
-    const size_t wbuf = PRUNE ? (size_t)sh.W * kSurvivorBuf * sizeof(RecT) : 0;
+    P.flush = get_option("flush", kSurvivorFlush);
+    if (P.flush < 32) P.flush = 32;
+    if (P.flush > 512) P.flush = 512;
+    P.flush = P.flush / kUnroll * kUnroll;
+    const size_t wbuf = PRUNE ? (size_t)sh.W * (P.flush + 32) * sizeof(RecT) : 0;
     const size_t bricks = (size_t)sh.nb * brick_bytes(D);
     const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
     const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
