@@ -415,7 +415,9 @@ def measure_job(job, ext, steps, warmup, flush, barrier, reduce_max, reduce_sum,
         E = reduce_sum(float(evals_local))
         executed = reduce_sum(float(executed_local))
         kernel_ms = reduce_max(eval_total / max(1, eval_n))
+        kernel_ms_mean = reduce_sum(eval_total / max(1, eval_n)) / job.world
         res[mode] = {"ms_per_step": total_ms / steps, "evals_per_step": E, "executed_per_step": executed,
+                     "kernel_ms_mean_over_ranks": kernel_ms_mean,
                      "kernel_ms_per_launch": kernel_ms, "seed_ms_per_launch": seed_total / max(1, seed_n),
                      "launches": int(reduce_sum(float(launches))), "evals_per_s": E / (total_ms / steps * 1e-3),
                      "kernel_evals_per_s": (E / job.world) / (kernel_ms * 1e-3),
@@ -569,6 +571,7 @@ def run_cuda(args):
             "achieved": exh["kernel_evals_per_s"] * slots / 1e12, "peak": peak_slots / 1e12, "unit": "Tslot/s",
             "frac": exh["kernel_frac"], "traffic": traffic,
             "slots_per_eval": slots, "evals_per_launch": E / world, "kernel_ms_per_launch": exh["kernel_ms_per_launch"],
+            "kernel_ms_mean_over_ranks": exh["kernel_ms_mean_over_ranks"],
             "kernel_evals_per_s": exh["kernel_evals_per_s"], "peak_evals_per_s": peak_slots / slots,
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
             "flop_view": {"achieved_tflops": exh["kernel_evals_per_s"] * (3 * dim - 1) / 1e12,
@@ -580,6 +583,7 @@ def run_cuda(args):
             "kernel": "cover_eval_kernel<D, PRUNE=true>, seed pass + full pass (what flood_complex runs by default)",
             "ms_per_step": dflt["ms_per_step"], "evals_per_s": dflt["evals_per_s"],
             "kernel_ms_per_launch": dflt["kernel_ms_per_launch"], "seed_ms_per_launch": dflt["seed_ms_per_launch"],
+            "kernel_ms_mean_over_ranks": dflt["kernel_ms_mean_over_ranks"],
             "executed_frac": executed_frac,
             "frac_of_issue_peak_on_executed_work": dflt["kernel_evals_per_s"] * executed_frac * slots / peak_slots,
             "algorithmic_speedup": exh["ms_per_step"] / dflt["ms_per_step"],
