@@ -869,7 +869,7 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     // sweep task = one brick x P.seg tile records; the exhaustive sweep has uniform tasks and
     // prefers long ones (fewer loop prologues), the pruned sweep short ones (balance)
     P.seg = get_option("seg", PRUNE ? 256 : 1024);
-    // dynamic shared memory: tile | staging rings | survivor buffers | bricks | boxes, bounds, cursors | runs
+    // dynamic shared memory: tile | staging rings / survivor buffers | bricks | boxes, bounds, cursors | runs
     const size_t staging = P.async_gather ? (size_t)sh.W * 2 * 32 * async_lpl(D) * sizeof(RecT) : 0;
     P.flush = get_option("flush", kSurvivorFlush);
     if (P.flush < 32) P.flush = 32;
@@ -879,7 +879,10 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     const size_t bricks = (size_t)sh.nb * brick_bytes(D);
     const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
     const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
-    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + staging + wbuf + bricks + misc + runs;
+    // the staging rings are live only while gathering, the survivor buffers only while sweeping:
+    // they share one region
+    const size_t scratch = staging > wbuf ? staging : wbuf;
+    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + scratch + bricks + misc + runs;
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
     long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
     const int cap_max = get_option("tile_cap_max", 8192);
@@ -898,8 +901,8 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
         P.seg = P.seg / kUnroll * kUnroll;
     }
     size_t o = (size_t)(cap + kUnroll) * sizeof(RecT);
-    P.off_stage = (int)o;   o += staging;
-    P.off_wbuf = (int)o;    o += wbuf;
+    P.off_stage = (int)o;
+    P.off_wbuf = (int)o;    o += scratch;
     P.off_bricks = (int)o;  o += bricks;
     P.off_misc = (int)o;    o += misc;
     P.off_runs = (int)o;    o += runs;
