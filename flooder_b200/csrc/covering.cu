@@ -10,18 +10,23 @@
 //     global atomic queue by persistent CTAs;
 //   * the candidate stream of a simplex is the concatenation of the cell-row runs its ball
 //     touches in the cell-sorted cloud (cloud.cu); a CTA enumerates the rows, prefix-sums the run
-//     lengths and gathers its window of the stream with a binary search per point;
+//     lengths and its warps stream their window of it in units of consecutive positions
+//     (coalesced loads, cp.async double-buffered for the 16-byte records of D <= 4);
 //   * every gathered point is tested against the ball (the reference predicate) and the
-//     survivors are compacted with warp ballots into a shared-memory tile of float4 records;
-//   * when the tile fills up, all warps sweep it: each thread keeps up to 8 sample points and their
-//     running minima in registers, tile records are broadcast LDS.128 reads, the distance is the
-//     direct difference form in FP32 (D sub, 1 mul, D-1 fma, 1 min per pair), issued as packed
-//     FP32x2 instructions and 3-input minima (sweep_tile);
-//   * by default the sweep is pruned exactly: a warp skips the tile records that are at least as
-//     far from the box of its samples as its largest running minimum (sweep_tile_pruned), after
+//     survivors are compacted with warp ballots into a shared-memory tile of records;
+//   * the samples of the block live in shared memory as bricks of up to 8 groups of 32; when the
+//     tile is full, (brick, tile segment) pairs are tasks that warps claim and steal; a warp
+//     holds the brick it works on in registers, tile records are broadcast LDS.128 reads, the
+//     distance is the direct difference form in FP32 (D sub, 1 mul, D-1 fma, 1 min per pair),
+//     issued as packed FP32x2 instructions and 3-input minima (sweep_tile);
+//   * by default the sweep is pruned exactly: per task the records that are at least as far from
+//     the box of the brick's samples as the brick's largest running minimum are skipped, after
 //     a seed pass over a sub-sampled stream has given every sample a finite bound;
 //   * the minima are merged into min_dist2 with an unsigned atomicMin (non-negative floats order
 //     like their bit patterns), because a simplex may be split over several chunks.
+//
+// This file holds the host entry points and the small planning kernels; the evaluation kernel
+// is in covering_kernels.cuh and is instantiated per ambient dimension in covering_d<N>.cu.
 //
 // The dense mask, the index lists and the (S, R, D) sample tensor never exist.
 #include "covering_kernels.cuh"

@@ -131,7 +131,7 @@ int flood_covering_radius_f32(const void *cloud_workspace, int64_t n, int d, con
  * flooder/core.py:182-188) should make every brick spatially compact: the exact pruning then skips
  * more candidates.  The result does not depend on the order.  Returns the number of bricks
  * (out_groups may be NULL to query it) or a negative error code.  Depends on the options in
- * effect ("prune", "shape", "warps"). */
+ * effect ("small_max_bricks", "small_shape", "warps"). */
 int flood_covering_bricks(int64_t R, int d, int32_t *out_groups, int capacity, int *bricks_per_block);
 
 /* Cost estimate: out_tested[s] = number of cloud points in the cell rows touched by ball s (an

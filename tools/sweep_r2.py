@@ -1,6 +1,6 @@
 """Round-2 kernel experiments on one GPU: kernel shapes, brick ordering, seed strides.
 
-    python tools/sweep_r2.py torus1m [cheese1m ...] -- "shape=1" "shape=0,bricks=0" ...
+    python tools/sweep_r2.py torus1m [cheese1m ...] -- "prune=0" "prune=1,bricks=0" "prune=1,async_gather=0" ...
 
 Every variant is a comma-separated list of library options (plus bricks=0/1 for the host-side
 sample order).  Prints kernel times (CUDA events inside the library) and executed/E.
