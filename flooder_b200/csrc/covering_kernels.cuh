@@ -10,6 +10,10 @@ namespace flood {
 constexpr int kUnroll = 4;       // candidates per inner-loop trip
 // cp.async gather: records per lane and staging buffer (one for the 32-byte records of D >= 5)
 __host__ __device__ constexpr int async_lpl(int d) { return d <= 4 ? 2 : 1; }
+// pruned sweep: records each lane box-tests per trip (two independent chains for the 16-byte
+// records; the 32-byte records of D >= 5 cost more registers and shared memory than the latency
+// hiding returns: measured)
+__host__ __device__ constexpr int box_test_ilp(int d) { return d <= 4 ? 2 : 1; }
 constexpr int kSurvivorFlush = 32;   // pruned sweep: survivors collected per warp before they are swept (default)
 
 struct CoverParams {
@@ -41,7 +45,7 @@ struct CoverParams {
     int nb;                  // bricks per sample block (shared-memory resident)
     int seg;                 // tile records per sweep task (work-stealing granularity)
     int flush;               // pruned sweep: survivors collected per warp before they are swept (multiple of 4;
-                             // the per-warp buffer holds flush + 32 records)
+                             // the per-warp buffer holds flush + 32 * box_test_ilp(D) records)
     int tile_cap;            // candidate records per shared-memory tile
     // dynamic shared memory layout (byte offsets; tile at 0)
     int off_stage, off_wbuf, off_bricks, off_misc, off_runs;
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     const int nb = P.nb;
     const int tile_cap = P.tile_cap;
     RecT *tile = reinterpret_cast<RecT *>(smem_raw);
-    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * (P.flush + 32);
+    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * (P.flush + 32 * box_test_ilp(D));
     float *bricks = reinterpret_cast<float *>(smem_raw + P.off_bricks);       // [nb][kMaxT][D+1][32]
     float *sbox = reinterpret_cast<float *>(smem_raw + P.off_misc);           // [nb][2D]
     unsigned *ub = reinterpret_cast<unsigned *>(sbox + nb * 2 * D);           // [nb] largest minimum per brick
@@ -723,10 +727,17 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
                     return v;
                 };
+                // Exhaustive sweep: segments are claimed one ahead (lane 0 holds the claim; it is
+                // broadcast when it is needed), so the atomic's latency overlaps the current segment.
+                // Pruned sweep: segments cost anything between nothing and a full sweep, a hoarded
+                // segment unbalances the end of the tile (measured: +7 %), so it claims on demand.
+                // (The same holds when a few bricks are shared by all warps: no claiming ahead.)
+                const bool ahead = !PRUNE && nb >= W;
+                int claim = 0;
+                if (ahead && lane == 0) claim = atomicAdd(&cursor[b], 1);
                 for (;;) {
-                    int seg = 0;
-                    if (lane == 0) seg = atomicAdd(&cursor[b], 1);
-                    seg = __shfl_sync(0xffffffffu, seg, 0);
+                    if (!ahead && lane == 0) claim = atomicAdd(&cursor[b], 1);
+                    const int seg = __shfl_sync(0xffffffffu, claim, 0);
                     if (seg >= nseg) {
                         if (have) {
                             // end of the stint on brick b: flush the survivors, merge the minima
@@ -762,8 +773,10 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         }
                         if (best <= 0) break;
                         b = who;
+                        if (ahead && lane == 0) claim = atomicAdd(&cursor[b], 1);
                         continue;
                     }
+                    if (ahead && lane == 0) claim = atomicAdd(&cursor[b], 1);   // the next segment of this brick
                     if (!have) {
                         int gf;
                         brick_span(blk_groups, nb, b, gf, nt);
@@ -786,32 +799,54 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         sweep_records<D>(tile + lo, (hi - lo + kUnroll - 1) / kUnroll * kUnroll, nt, x, m);
                         swept += (unsigned)(hi - lo);
                     }
-                    for (int base = lo; PRUNE && base < hi; base += 32) {
-                        const int idx = base + lane;
-                        const RecT rec = tile[idx < hi ? idx : tile_cap];
-                        float own[D];
-                        rec_unpack<D>(rec, own);
-                        float box2 = 0.f;
+                    // box test, two records per lane and trip (independent chains hide each other's
+                    // latency: with 5 warps per sub-partition the test loop is latency-bound)
+                    constexpr int TI = box_test_ilp(D);
+                    for (int base = lo; PRUNE && base < hi; base += 32 * TI) {
+                        RecT rec[TI];
+                        bool keep[TI];
 #pragma unroll
-                        for (int a = 0; a < D; ++a) {
-                            const float e = fmaxf(fmaxf(blo[a] - own[a], own[a] - bhi[a]), 0.f);
-                            box2 = fmaf(e, e, box2);
+                        for (int v = 0; v < TI; ++v) {
+                            const int idx = base + 32 * v + lane;
+                            rec[v] = tile[idx < hi ? idx : tile_cap];
+                            float own[D];
+                            rec_unpack<D>(rec[v], own);
+                            float box2 = 0.f;
+#pragma unroll
+                            for (int a = 0; a < D; ++a) {
+                                const float e = fmaxf(fmaxf(blo[a] - own[a], own[a] - bhi[a]), 0.f);
+                                box2 = fmaf(e, e, box2);
+                            }
+                            // 0.9999: the box distance and the pair distances are rounded differently
+                            keep[v] = idx < hi && box2 * 0.9999f <= u;
                         }
-                        // 0.9999: the box distance and the pair distances are rounded differently
-                        const bool keep = idx < hi && box2 * 0.9999f <= u;
-                        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-                        if (mask == 0u) continue;
-                        if (keep) wbuf[cnt + __popc(mask & lt_mask)] = rec;
-                        cnt += __popc(mask);
+                        unsigned mask[TI], any = 0u;
+#pragma unroll
+                        for (int v = 0; v < TI; ++v) {
+                            mask[v] = __ballot_sync(0xffffffffu, keep[v]);
+                            any |= mask[v];
+                        }
+                        if (any == 0u) continue;
+#pragma unroll
+                        for (int v = 0; v < TI; ++v) {
+                            if (keep[v]) wbuf[cnt + __popc(mask[v] & lt_mask)] = rec[v];
+                            cnt += __popc(mask[v]);
+                        }
                         if (cnt >= P.flush) {
+                            const int nsweep = cnt / P.flush * P.flush;
                             __syncwarp();
-                            sweep_records<D>(wbuf, P.flush, nt, x, m);
-                            swept += (unsigned)P.flush;
-                            cnt -= P.flush;
-                            RecT carry_rec;
-                            if (lane < cnt) carry_rec = wbuf[P.flush + lane];
-                            __syncwarp();
-                            if (lane < cnt) wbuf[lane] = carry_rec;
+                            sweep_records<D>(wbuf, nsweep, nt, x, m);
+                            swept += (unsigned)nsweep;
+                            cnt -= nsweep;
+                            // carry the rest (< flush) to the front, 32 records at a time (a chunk's
+                            // destination ends where its source begins or earlier: nsweep >= 32)
+                            for (int k0 = 0; k0 < cnt; k0 += 32) {
+                                RecT carry_rec;
+                                if (k0 + lane < cnt) carry_rec = wbuf[nsweep + k0 + lane];
+                                __syncwarp();
+                                if (k0 + lane < cnt) wbuf[k0 + lane] = carry_rec;
+                                __syncwarp();
+                            }
                             u = bound();
                         }
                     }
@@ -875,7 +910,7 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     if (P.flush < 32) P.flush = 32;
     if (P.flush > 512) P.flush = 512;
     P.flush = P.flush / kUnroll * kUnroll;
-    const size_t wbuf = PRUNE ? (size_t)sh.W * (P.flush + 32) * sizeof(RecT) : 0;
+    const size_t wbuf = PRUNE ? (size_t)sh.W * (P.flush + 32 * box_test_ilp(D)) * sizeof(RecT) : 0;
     const size_t bricks = (size_t)sh.nb * brick_bytes(D);
     const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
     const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
