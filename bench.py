@@ -654,7 +654,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference", "reference_triton"])
     ap.add_argument("--workload", default="torus_1m_1k", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--config-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-simplices", type=int, default=400)
     ap.add_argument("--ref-simplices-per-step", type=int, default=200)
