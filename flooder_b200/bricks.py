@@ -60,8 +60,9 @@ def brick_order(weights: np.ndarray, brick_groups: Sequence[int], bricks_per_blo
     """Permutation ``perm`` (int64, length R): ``weights[perm]`` is the order to hand to the kernel.
 
     ``brick_groups[i]`` = number of ``group``-sample groups of brick i, ``bricks_per_block``
-    consecutive bricks form one CTA's sample block (``flood_covering_bricks``).  Three nested
-    bisections: sample blocks, bricks inside a block, groups inside a brick."""
+    consecutive bricks form one CTA's sample block (``flood_covering_bricks``).  Nested
+    bisections: sample blocks, bricks inside a block, pairs of groups inside a brick, the two
+    groups of a pair."""
     w = np.asarray(weights, dtype=np.float64)
     R = w.shape[0]
     w = np.round(w @ split_directions(w.shape[1]).T, 9)      # rounding keeps lattice ties exact
@@ -81,7 +82,12 @@ def brick_order(weights: np.ndarray, brick_groups: Sequence[int], bricks_per_blo
         _bisect(w, idx_b, bricks, brick_idx)
         for idx_k in brick_idx:
             if idx_k.size:
-                _bisect(w, idx_k, _segments(idx_k.size, group), pieces)
+                # pairs of groups first (the kernel's second-level boxes are those of groups
+                # (0,1), (2,3), ... of a brick), then the two groups of a pair
+                pair_idx: List[np.ndarray] = []
+                _bisect(w, idx_k, _segments(idx_k.size, 2 * group), pair_idx)
+                for idx_p in pair_idx:
+                    _bisect(w, idx_p, _segments(idx_p.size, group), pieces)
     perm = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.int64)
     assert perm.size == R
     return perm

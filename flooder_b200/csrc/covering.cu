@@ -259,15 +259,18 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
     P.evals = out_evals;
     P.tested = reinterpret_cast<int *>(wbase + L.off_tested);
     P.item_base = reinterpret_cast<long long *>(wbase + L.off_item_base);
+    // target tested points per work item: the pruned sweep executes a fraction of a chunk's
+    // evaluations and amortises its per-item work (brick load, bounds, merges) over longer chunks
+    const bool prune = get_option("prune", 1) != 0;
+    const int chunk_default = prune ? 32768 : 16384;
     {
         // the seed pass (pruned mode) takes every seed_stride-th record: its chunks are that much
         // longer, so that a seed item carries as many records as an item of the full pass
-        const bool prune = get_option("prune", 1) != 0;
         const long long seed_stride = get_option("seed_stride", 32);
         const long long mult = get_option("seed_chunk_mult", 0) > 0 ? get_option("seed_chunk_mult", 0) : seed_stride;
         if (prune && seed_stride > 1 && mult > 1) {
             P.item_base_seed = reinterpret_cast<long long *>(wbase + L.off_item_base_seed);
-            long long cs = (long long)(get_option("chunk", 16384) < 256 ? 256 : get_option("chunk", 16384)) * mult;
+            long long cs = (long long)(get_option("chunk", chunk_default) < 256 ? 256 : get_option("chunk", chunk_default)) * mult;
             P.chunk_seed = (int)(cs > (1ll << 30) ? (1ll << 30) : cs);
         }
     }
@@ -277,7 +280,7 @@ int covering_radius(const void *cloud_ws, int64_t n, int d, const float *verts, 
     P.R = R;
     P.K = K;
     P.nsb = 1;
-    P.chunk = get_option("chunk", 16384);
+    P.chunk = get_option("chunk", chunk_default);
     if (P.chunk < 256) P.chunk = 256;
     P.rows_per_chunk_factor = get_option("rows_per_chunk_factor", 32);
 

@@ -47,6 +47,11 @@ struct CoverParams {
     int flush;               // pruned sweep: survivors collected per warp before they are swept (multiple of 4;
                              // the per-warp buffer holds flush + 32 * box_test_ilp(D) records)
     int tile_cap;            // candidate records per shared-memory tile
+    int level2;              // pruned sweep: survivors of the brick test are re-tested per pair of groups
+    int slab_cull;           // pruned sweep: whole slabs of tile records are skipped by their bounding box
+    int l2_bypass;           // second level: units whose pair-survivor share is >= l2_bypass/8 take the whole-brick sweep
+    int off_slab;            // shared-memory offset of the slab boxes
+    int wbuf_stride;         // records of per-warp scratch (survivor buffer + second-level buffer)
     // dynamic shared memory layout (byte offsets; tile at 0)
     int off_stage, off_wbuf, off_bricks, off_misc, off_runs;
     int chunk;               // target tested points per chunk
@@ -134,6 +139,7 @@ __device__ __forceinline__ void row_run(const BallCells<G> &b, int row, const Gr
 //   narrow   4 warps, 5 CTAs per SM  } sweep phases; the warps share the bricks segment by segment
 constexpr int kMaxT = 8;            // sample groups per brick (register-resident while swept)
 constexpr int kWideWarps = 20;
+constexpr int kWidePrunedWarps = 16;
 constexpr int kMediumWarps = 8;
 constexpr int kMediumCtas = 2;
 constexpr int kNarrowWarps = 4;
@@ -194,6 +200,16 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// order-preserving map float -> unsigned (and back): lets REDUX (integer warp reduction) take
+// minima / maxima of signed floats
+__device__ __forceinline__ unsigned float_key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 // squared distance, direct difference form: (x0-p0)^2 rounded, then FMA accumulation
 template <int D>
 __device__ __forceinline__ float dist2(const float (&x)[D], const float (&p)[D]) {
@@ -243,18 +259,36 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &
 // for four evaluations.  An odd group is handled with the scalar form.  Each lane result is the
 // same IEEE operation as the scalar form (x - p, round; *, round; fma, round), so the minima are
 // bit-identical to a scalar evaluation.
-template <int D, int NT_, int MAXT>
+template <int D, int NT_, int MAXT, int T0 = 0, bool PREFETCH = false>
 __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restrict__ tile, int npad,
                                            const float (&x)[MAXT][D], float (&m)[MAXT]) {
+    // sweeps groups T0 .. T0+NT_-1 of the brick held in registers.  PREFETCH (the two-group sweeps
+    // of the pruned path: 28 arithmetic instructions per trip do not cover the LDS latency) loads
+    // the next trip's records before the current trip's arithmetic.
+    float pn[kUnroll][D];
+    if (PREFETCH) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[u], pn[u]);
+    }
 #pragma unroll 1
     for (int j = 0; j < npad; j += kUnroll) {
         float p[kUnroll][D];
+        if (PREFETCH) {
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
+            for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                for (int a = 0; a < D; ++a) p[u][a] = pn[u][a];
+            const int jn = min(j + kUnroll, npad - kUnroll);   // the last trip re-reads itself
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[jn + u], pn[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) rec_unpack<D>(tile[j + u], p[u]);
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; u += 2) {
 #pragma unroll
-            for (int t = 0; t + 1 < NT_; t += 2) {
+            for (int t = T0; t + 1 < T0 + NT_; t += 2) {
                 float2 acc[2];
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
@@ -272,7 +306,7 @@ __device__ __forceinline__ void sweep_tile(const typename Rec<D>::type *__restri
                 m[t + 1] = fmin3(m[t + 1], acc[0].y, acc[1].y);
             }
             if (NT_ & 1) {
-                constexpr int t = NT_ - 1;
+                constexpr int t = T0 + NT_ - 1;
                 m[t] = fmin3(m[t], dist2<D>(x[t], p[u]), dist2<D>(x[t], p[u + 1]));
             }
         }
@@ -546,11 +580,14 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     const int nb = P.nb;
     const int tile_cap = P.tile_cap;
     RecT *tile = reinterpret_cast<RecT *>(smem_raw);
-    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * (P.flush + 32 * box_test_ilp(D));
+    RecT *wbuf = reinterpret_cast<RecT *>(smem_raw + P.off_wbuf) + (size_t)warp * P.wbuf_stride;
+    RecT *wbuf2 = wbuf + P.flush + 32 * box_test_ilp(D);   // second-level survivors (32 * box_test_ilp(D) + kUnroll records)
+    float *slabbox = reinterpret_cast<float *>(smem_raw + P.off_slab);        // [tile slabs][2D] boxes of the tile's slabs
     float *bricks = reinterpret_cast<float *>(smem_raw + P.off_bricks);       // [nb][kMaxT][D+1][32]
     float *sbox = reinterpret_cast<float *>(smem_raw + P.off_misc);           // [nb][2D]
     unsigned *ub = reinterpret_cast<unsigned *>(sbox + nb * 2 * D);           // [nb] largest minimum per brick
     int *cursor = reinterpret_cast<int *>(ub + nb);                           // [nb] next unclaimed segment
+    float *sbox2 = reinterpret_cast<float *>(cursor + nb);                    // [nb][kMaxT/2][2D] boxes of the pairs of groups
     int *run_start = reinterpret_cast<int *>(smem_raw + P.off_runs);
     __shared__ int warp_sums[32];
     __shared__ int s_fill;
@@ -632,9 +669,9 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
         for (int b = warp; b < nb; b += W) {
             int gf, gc;
             brick_span(blk_groups, nb, b, gf, gc);
-            float lo[D], hi[D], u = 0.f;
+            float lo[D], hi[D], plo[D], phi[D], u = 0.f;
 #pragma unroll
-            for (int a = 0; a < D; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+            for (int a = 0; a < D; ++a) { lo[a] = plo[a] = INFINITY; hi[a] = phi[a] = -INFINITY; }
             for (int t = 0; t < kMaxT; ++t) {
                 const long long r = (long long)(blk_g0 + gf + t) * 32 + lane;
                 const bool valid = t < gc && r < P.R;
@@ -661,23 +698,38 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         }
                     }
 #pragma unroll
-                    for (int a = 0; a < D; ++a) { lo[a] = fminf(lo[a], x[a]); hi[a] = fmaxf(hi[a], x[a]); }
+                    for (int a = 0; a < D; ++a) { plo[a] = fminf(plo[a], x[a]); phi[a] = fmaxf(phi[a], x[a]); }
                 }
                 float *g = bricks + ((size_t)b * kMaxT + t) * XS;
 #pragma unroll
                 for (int a = 0; a < D; ++a) g[a * 32 + lane] = x[a];
                 g[D * 32 + lane] = mval;
                 u = fmaxf(u, mval);
+                if (PRUNE && (t & 1)) {
+                    // box of the pair of groups (t-1, t): the second-level test of the pruned sweep
+                    // (an empty pair keeps the inverted box, which no record is near)
+#pragma unroll
+                    for (int a = 0; a < D; ++a) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            plo[a] = fminf(plo[a], __shfl_xor_sync(0xffffffffu, plo[a], o));
+                            phi[a] = fmaxf(phi[a], __shfl_xor_sync(0xffffffffu, phi[a], o));
+                        }
+                        if (lane == 0) {
+                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + a] = plo[a];
+                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + D + a] = phi[a];
+                        }
+                        lo[a] = fminf(lo[a], plo[a]);
+                        hi[a] = fmaxf(hi[a], phi[a]);
+                        plo[a] = INFINITY;
+                        phi[a] = -INFINITY;
+                    }
+                }
             }
             if (PRUNE) {
+                if (lane == 0) {
 #pragma unroll
-                for (int a = 0; a < D; ++a) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-                        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-                    }
-                    if (lane == 0) { sbox[b * 2 * D + a] = lo[a]; sbox[b * 2 * D + D + a] = hi[a]; }
+                    for (int a = 0; a < D; ++a) { sbox[b * 2 * D + a] = lo[a]; sbox[b * 2 * D + D + a] = hi[a]; }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
@@ -710,12 +762,45 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     if (tid < npad - n) tile[n + tid] = rec_sentinel<D>();
                     __syncthreads();
                 }
+                constexpr int SL = 32 * box_test_ilp(D);   // records per slab = per trip of the brick test
+                if (PRUNE && P.slab_cull) {
+                    // bounding boxes of the tile's slabs (the stream is in cell order, a slab is a
+                    // few neighbouring cells): a task skips the slabs whose box is out of its brick's reach
+                    const int nslab = (n + SL - 1) / SL;
+                    for (int sl = warp; sl < nslab; sl += W) {
+                        float lo[D], hi[D];
+#pragma unroll
+                        for (int a = 0; a < D; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+#pragma unroll
+                        for (int v = 0; v < SL / 32; ++v) {
+                            const int idx = sl * SL + 32 * v + lane;
+                            if (idx < n) {
+                                float q[D];
+                                rec_unpack<D>(tile[idx], q);
+#pragma unroll
+                                for (int a = 0; a < D; ++a) { lo[a] = fminf(lo[a], q[a]); hi[a] = fmaxf(hi[a], q[a]); }
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < D; ++a) {
+                            // order-preserving float -> unsigned key, one REDUX per bound
+                            const unsigned kl = __reduce_min_sync(0xffffffffu, float_key(lo[a]));
+                            const unsigned kh = __reduce_max_sync(0xffffffffu, float_key(hi[a]));
+                            if (lane == 0) {
+                                slabbox[(size_t)sl * 2 * D + a] = key_float(kl);
+                                slabbox[(size_t)sl * 2 * D + D + a] = key_float(kh);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
                 const int seg_len = P.seg;
                 const int nseg = (n + seg_len - 1) / seg_len;
                 int b = warp % nb;
                 bool have = false;     // registers hold brick b
                 int cnt = 0, nt = 0;   // survivors waiting in wbuf; groups of brick b
                 unsigned long long swept = 0;   // records swept for brick b in this stint
+                unsigned swept_groups = 0;      // second level: (record, group) pairs swept in this stint
                 float x[kMaxT][D], m[kMaxT], blo[D], bhi[D], u = 0.f;
 #pragma unroll
                 for (int t = 0; t < kMaxT; ++t) m[t] = 0.f;
@@ -726,6 +811,109 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
                     return v;
+                };
+                // Second level of the pruned sweep: the survivors of the brick test (up to 32 records
+                // at src) are tested against the boxes of the brick's pairs of groups (64 samples,
+                // bound = the pair's largest running minimum), compacted per pair and swept with the
+                // two-group loop.  Finer boxes and bounds skip about half of the evaluations the
+                // brick-level rule alone would execute; the brick test keeps the cost of the fine
+                // tests proportional to the survivors.
+                constexpr int NP = kMaxT / 2;
+                float uj[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) uj[j] = 0.f;
+                auto pair_bound = [&](int j) {
+                    // non-negative floats order like their bit patterns: one REDUX
+                    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m[2 * j], m[2 * j + 1]))));
+                };
+                constexpr int TI2 = box_test_ilp(D);       // records per lane in a unit
+                constexpr int UNIT2 = 32 * TI2;
+                auto sweep_unit = [&](const RecT *src, int n_u) {
+                    RecT rec[TI2];
+                    unsigned mk[NP][TI2];
+#pragma unroll
+                    for (int v = 0; v < TI2; ++v) {
+                        const bool inr = lane + 32 * v < n_u;
+                        rec[v] = src[inr ? lane + 32 * v : 0];
+                        float q[D];
+                        rec_unpack<D>(rec[v], q);
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) {
+                            mk[j][v] = 0u;
+                            if (2 * j < nt) {
+                                const float *bx = sbox2 + ((size_t)b * NP + j) * 2 * D;
+                                float box2 = 0.f;
+#pragma unroll
+                                for (int a = 0; a < D; ++a) {
+                                    const float e = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[D + a]), 0.f);
+                                    box2 = fmaf(e, e, box2);
+                                }
+                                mk[j][v] = __ballot_sync(0xffffffffu, inr && box2 * 0.9999f <= uj[j]);
+                            }
+                        }
+                    }
+                    {
+                        // nearly every record is near nearly every pair (first tiles of a seed pass,
+                        // bricks in sparse regions): one sweep with the whole brick, no compaction
+                        int tot = 0;
+#pragma unroll
+                        for (int j = 0; j < NP; ++j)
+#pragma unroll
+                            for (int v = 0; v < TI2; ++v) tot += __popc(mk[j][v]);
+                        if (tot * 8 >= P.l2_bypass * n_u * ((nt + 1) >> 1)) {
+                            const int npad = (n_u + kUnroll - 1) / kUnroll * kUnroll;
+                            // (a partial unit is the last of the buffer: the slots behind it are free)
+                            if (lane < npad - n_u) const_cast<RecT *>(src)[n_u + lane] = rec_sentinel<D>();
+                            __syncwarp();
+                            sweep_records<D>(src, npad, nt, x, m);
+                            swept += (unsigned)n_u;
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) uj[j] = pair_bound(j);
+                            float v = uj[0];
+#pragma unroll
+                            for (int j = 1; j < NP; ++j) v = fmaxf(v, uj[j]);
+                            u = v;
+                            return;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        int c2 = 0;
+#pragma unroll
+                        for (int v = 0; v < TI2; ++v) c2 += __popc(mk[j][v]);
+                        if (c2 == 0) continue;
+                        const int pad = (-c2) & (kUnroll - 1);
+                        __syncwarp();   // the previous pair's sweep has read wbuf2
+                        int off = 0;
+#pragma unroll
+                        for (int v = 0; v < TI2; ++v) {
+                            if ((mk[j][v] >> lane) & 1u) wbuf2[off + __popc(mk[j][v] & lt_mask)] = rec[v];
+                            off += __popc(mk[j][v]);
+                        }
+                        if (lane < pad) wbuf2[c2 + lane] = rec_sentinel<D>();
+                        __syncwarp();
+                        if (P.level2 & 2) {
+                            switch (j) {
+                                case 0: sweep_tile<D, 2, kMaxT, 0, true>(wbuf2, c2 + pad, x, m); break;
+                                case 1: sweep_tile<D, 2, kMaxT, 2, true>(wbuf2, c2 + pad, x, m); break;
+                                case 2: sweep_tile<D, 2, kMaxT, 4, true>(wbuf2, c2 + pad, x, m); break;
+                                default: sweep_tile<D, 2, kMaxT, 6, true>(wbuf2, c2 + pad, x, m); break;
+                            }
+                        } else {
+                            switch (j) {
+                                case 0: sweep_tile<D, 2, kMaxT, 0>(wbuf2, c2 + pad, x, m); break;
+                                case 1: sweep_tile<D, 2, kMaxT, 2>(wbuf2, c2 + pad, x, m); break;
+                                case 2: sweep_tile<D, 2, kMaxT, 4>(wbuf2, c2 + pad, x, m); break;
+                                default: sweep_tile<D, 2, kMaxT, 6>(wbuf2, c2 + pad, x, m); break;
+                            }
+                        }
+                        swept_groups += (unsigned)(c2 * min(2, nt - 2 * j));
+                        uj[j] = pair_bound(j);
+                    }
+                    float v = uj[0];
+#pragma unroll
+                    for (int j = 1; j < NP; ++j) v = fmaxf(v, uj[j]);
+                    u = v;
                 };
                 // Exhaustive sweep: segments are claimed one ahead (lane 0 holds the claim; it is
                 // broadcast when it is needed), so the atomic's latency overlaps the current segment.
@@ -742,12 +930,17 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         if (have) {
                             // end of the stint on brick b: flush the survivors, merge the minima
                             if (PRUNE && cnt > 0) {
-                                const int npad = (cnt + kUnroll - 1) / kUnroll * kUnroll;
-                                if (lane < npad - cnt) wbuf[cnt + lane] = rec_sentinel<D>();
                                 __syncwarp();
-                                sweep_records<D>(wbuf, npad, nt, x, m);
+                                if (P.level2) {
+                                    for (int k0 = 0; k0 < cnt; k0 += UNIT2) sweep_unit(wbuf + k0, min(UNIT2, cnt - k0));
+                                } else {
+                                    const int npad = (cnt + kUnroll - 1) / kUnroll * kUnroll;
+                                    if (lane < npad - cnt) wbuf[cnt + lane] = rec_sentinel<D>();
+                                    __syncwarp();
+                                    sweep_records<D>(wbuf, npad, nt, x, m);
+                                    swept += (unsigned)cnt;
+                                }
                                 __syncwarp();
-                                swept += (unsigned)cnt;
                                 cnt = 0;
                             }
 #pragma unroll
@@ -759,8 +952,9 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                                 const float v = bound();
                                 if (lane == 0) atomicMin(&ub[b], __float_as_uint(v));
                             }
-                            executed_evals += swept * (unsigned long long)(nt * 32);
+                            executed_evals += swept * (unsigned long long)(nt * 32) + 32ull * swept_groups;
                             swept = 0;
+                            swept_groups = 0;
                             have = false;
                         }
                         // steal from the brick with the most unclaimed segments
@@ -791,6 +985,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
 #pragma unroll
                             for (int a = 0; a < D; ++a) { blo[a] = sbox[b * 2 * D + a]; bhi[a] = sbox[b * 2 * D + D + a]; }
                             u = bound();
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) uj[j] = pair_bound(j);
                         }
                         have = true;
                     }
@@ -802,7 +998,25 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     // box test, two records per lane and trip (independent chains hide each other's
                     // latency: with 5 warps per sub-partition the test loop is latency-bound)
                     constexpr int TI = box_test_ilp(D);
-                    for (int base = lo; PRUNE && base < hi; base += 32 * TI) {
+                    unsigned live = 0u;   // slabs of the segment (bit k = records lo + k*SL ...) the brick can reach
+                    if (PRUNE) {
+                        const int ns = (hi - lo + SL - 1) / SL;        // <= 32 (P.seg <= 32 * SL)
+                        bool reach = lane < ns;
+                        if (P.slab_cull && reach) {
+                            const float *sb = slabbox + (size_t)(lo / SL + lane) * 2 * D;
+                            float box2 = 0.f;
+#pragma unroll
+                            for (int a = 0; a < D; ++a) {
+                                const float e = fmaxf(fmaxf(blo[a] - sb[D + a], sb[a] - bhi[a]), 0.f);
+                                box2 = fmaf(e, e, box2);
+                            }
+                            reach = box2 * 0.9999f <= u;   // every record of the slab is at least that far
+                        }
+                        live = __ballot_sync(0xffffffffu, reach);
+                    }
+                    while (live) {
+                        const int base = lo + (__ffs(live) - 1) * SL;
+                        live &= live - 1u;
                         RecT rec[TI];
                         bool keep[TI];
 #pragma unroll
@@ -835,8 +1049,13 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         if (cnt >= P.flush) {
                             const int nsweep = cnt / P.flush * P.flush;
                             __syncwarp();
-                            sweep_records<D>(wbuf, nsweep, nt, x, m);
-                            swept += (unsigned)nsweep;
+                            if (P.level2) {
+                                for (int k0 = 0; k0 < nsweep; k0 += UNIT2) sweep_unit(wbuf + k0, UNIT2);
+                                __syncwarp();
+                            } else {
+                                sweep_records<D>(wbuf, nsweep, nt, x, m);
+                                swept += (unsigned)nsweep;
+                            }
                             cnt -= nsweep;
                             // carry the rest (< flush) to the front, 32 records at a time (a chunk's
                             // destination ends where its source begins or earlier: nsweep >= 32)
@@ -847,7 +1066,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                                 if (k0 + lane < cnt) wbuf[k0 + lane] = carry_rec;
                                 __syncwarp();
                             }
-                            u = bound();
+                            if (!P.level2) u = bound();
                         }
                     }
                 }
@@ -910,16 +1129,29 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     if (P.flush < 32) P.flush = 32;
     if (P.flush > 512) P.flush = 512;
     P.flush = P.flush / kUnroll * kUnroll;
-    const size_t wbuf = PRUNE ? (size_t)sh.W * (P.flush + 32 * box_test_ilp(D)) * sizeof(RecT) : 0;
+    // second level of the pruned sweep (per pair of groups); it takes the survivors 32 at a time
+    // level2: 0 off, 1 on, 3 on with prefetching two-group sweeps.  Default: on for the wide shape
+    // (measured in 5-D with the narrow shape: 2.5 x fewer evaluations executed, 10 % slower)
+    P.level2 = PRUNE ? get_option("level2", sh.minb == 1 ? 3 : 0) : 0;
+    P.l2_bypass = get_option("l2_bypass", 7);
+    P.slab_cull = PRUNE && get_option("slab_cull", sh.minb == 1 ? 1 : 0) != 0;   // (narrow shape in 5-D: 5 % slower with it)
+    constexpr int SL = 32 * box_test_ilp(D);     // records per unit of the second level = per slab of the tile
+    if (P.level2) {
+        if (get_option("flush", 0) <= 0) P.flush = SL;
+        P.flush = (P.flush + SL - 1) / SL * SL;
+    }
+    P.wbuf_stride = P.flush + SL + (P.level2 ? SL + kUnroll : 0);
+    const size_t wbuf = PRUNE ? (size_t)sh.W * P.wbuf_stride * sizeof(RecT) : 0;
     const size_t bricks = (size_t)sh.nb * brick_bytes(D);
-    const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
+    const size_t misc = ((size_t)sh.nb * (2 * D + 2 + (kMaxT / 2) * 2 * D) * 4 + 15) / 16 * 16;
     const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
     // the staging rings are live only while gathering, the survivor buffers only while sweeping:
     // they share one region
     const size_t scratch = staging > wbuf ? staging : wbuf;
-    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + scratch + bricks + misc + runs;
+    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + scratch + bricks + misc + runs + (P.slab_cull ? 16 + 2 * D * 4 : 0);
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
-    long long cap = (budget - (long long)fixed) / (long long)sizeof(RecT);
+    // a tile record costs its bytes plus its share of a slab box
+    long long cap = (budget - (long long)fixed) * SL / ((long long)sizeof(RecT) * SL + (P.slab_cull ? 2 * D * 4 : 0));
     const int cap_max = get_option("tile_cap_max", 8192);
     if (cap > cap_max) cap = cap_max;
     const int forced_cap = get_option("tile_cap", 0);   // experiments: a smaller tile (at least 2 records per thread)
@@ -934,6 +1166,11 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
         if (get_option("seg", 0) <= 0 && P.seg > balanced) P.seg = (int)balanced;
         if (P.seg < 32) P.seg = 32;
         P.seg = P.seg / kUnroll * kUnroll;
+        if (PRUNE) {
+            // pruned sweep: a segment is a whole number of slabs (at most 32: one lane per slab)
+            P.seg = (P.seg + SL - 1) / SL * SL;
+            if (P.seg > 32 * SL) P.seg = 32 * SL;
+        }
     }
     size_t o = (size_t)(cap + kUnroll) * sizeof(RecT);
     P.off_stage = (int)o;
@@ -941,6 +1178,8 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     P.off_bricks = (int)o;  o += bricks;
     P.off_misc = (int)o;    o += misc;
     P.off_runs = (int)o;    o += runs;
+    P.off_slab = (int)o;
+    if (P.slab_cull) o += ((size_t)(cap / SL + 1) * 2 * D * 4 + 15) / 16 * 16;
     const size_t smem = o;
     FLOOD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -982,6 +1221,20 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     const bool prune = get_option("prune", 1) != 0;
     const EvalShape sh = eval_shape(R, D);
     if (sh.minb == 1) {
+        // The exhaustive sweep is bound by the FMA pipe and wants every warp it can get (20 x 96
+        // registers); the pruned sweep is a chain of short dependent phases (box tests, compaction,
+        // two-group sweeps) that the compiler schedules much better with 128 registers: 16 warps
+        // (measured: 20 warps 52 ms, 16 warps 42.6 ms, 12 warps 43.5 ms on torus 1 M / 1 k).
+        const int ww = get_option("wide_warps", prune ? kWidePrunedWarps : kWideWarps);
+        if (ww == 16 || ww == 12) {
+            EvalShape sh2 = sh;
+            if (sh2.W > ww) sh2.W = ww;
+            if (ww == 16) {
+                if (prune) return launch_eval_shape<D, true, 16, 1>(P, sh2, st);
+                return launch_eval_shape<D, false, 16, 1>(P, sh2, st);
+            }
+            if (prune) return launch_eval_shape<D, true, 12, 1>(P, sh2, st);
+        }
         if (prune) return launch_eval_shape<D, true, kWideWarps, 1>(P, sh, st);
         return launch_eval_shape<D, false, kWideWarps, 1>(P, sh, st);
     }
