@@ -588,9 +588,11 @@ def run_cuda(args):
             "frac_of_issue_peak_on_executed_work": dflt["kernel_evals_per_s"] * executed_frac * slots / peak_slots,
             "algorithmic_speedup": exh["ms_per_step"] / dflt["ms_per_step"],
             "traffic": traffic_pruned, "gpu_launches": dflt["launches"],
-            "note": "exact pruning (SURVEY 8(f2)): a warp skips candidates that are at least as far from the box of "
-                    "its sample brick as its largest running minimum; minima are bit-identical to the exhaustive "
-                    "sweep, executed_frac of the algorithmic evaluations E is performed",
+            "note": "exact pruning (SURVEY 8(f2)), two levels: a warp skips candidates that are at least as far "
+                    "from the box of its sample brick (256 samples) as the brick's largest running minimum, and the "
+                    "survivors are re-tested against the boxes and bounds of the brick's pairs of 32-sample groups; "
+                    "minima are bit-identical to the exhaustive sweep, executed_frac of the algorithmic evaluations "
+                    "E is performed",
         }
         fps_ms = fps_ms_total / max(1, fps_launches)
         fps_bytes = float(n) * (4 * dim + 8) * (n_lms - 1)      # N (4D + 8) per iteration

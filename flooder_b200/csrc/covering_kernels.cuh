@@ -145,6 +145,9 @@ constexpr int kMediumCtas = 2;
 constexpr int kNarrowWarps = 4;
 constexpr int kNarrowCtas = 5;
 constexpr int kMaxBricks = 20;      // bricks per CTA (<= 32: one lane per brick when stealing)
+// CTAs per SM of the shapes whose pruned kernel carries the second-level code (wide; the
+// experimental 4 x 4-warp narrow shape)
+__host__ __device__ constexpr bool eval_shape_has_level2(int minb) { return minb == 1 || minb == 4; }
 
 struct EvalShape {
     int W;        // warps per CTA
@@ -572,6 +575,11 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     using RecT = typename Rec<D>::type;
     using StreamT = Stream<D>;
     constexpr int XS = (D + 1) * 32;           // floats per (brick, group): D coordinate rows + the minima row
+    // the second level of the pruned sweep and the slab culling are compiled for the shapes that use
+    // them (the 96-register narrow / medium kernels spill heavily with that code in them)
+    constexpr bool L2 = PRUNE && eval_shape_has_level2(MINB);
+    const int level2 = L2 ? P.level2 : 0;
+    const bool slab_cull = L2 && P.slab_cull;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             plo[a] = fminf(plo[a], __shfl_xor_sync(0xffffffffu, plo[a], o));
                             phi[a] = fmaxf(phi[a], __shfl_xor_sync(0xffffffffu, phi[a], o));
                         }
-                        if (lane == 0) {
+                        if (L2 && lane == 0) {
                             sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + a] = plo[a];
                             sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + D + a] = phi[a];
                         }
@@ -763,7 +771,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     __syncthreads();
                 }
                 constexpr int SL = 32 * box_test_ilp(D);   // records per slab = per trip of the brick test
-                if (PRUNE && P.slab_cull) {
+                if (slab_cull) {
                     // bounding boxes of the tile's slabs (the stream is in cell order, a slab is a
                     // few neighbouring cells): a task skips the slabs whose box is out of its brick's reach
                     const int nslab = (n + SL - 1) / SL;
@@ -892,7 +900,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         }
                         if (lane < pad) wbuf2[c2 + lane] = rec_sentinel<D>();
                         __syncwarp();
-                        if (P.level2 & 2) {
+                        if (level2 & 2) {
                             switch (j) {
                                 case 0: sweep_tile<D, 2, kMaxT, 0, true>(wbuf2, c2 + pad, x, m); break;
                                 case 1: sweep_tile<D, 2, kMaxT, 2, true>(wbuf2, c2 + pad, x, m); break;
@@ -931,7 +939,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             // end of the stint on brick b: flush the survivors, merge the minima
                             if (PRUNE && cnt > 0) {
                                 __syncwarp();
-                                if (P.level2) {
+                                if (level2) {
                                     for (int k0 = 0; k0 < cnt; k0 += UNIT2) sweep_unit(wbuf + k0, min(UNIT2, cnt - k0));
                                 } else {
                                     const int npad = (cnt + kUnroll - 1) / kUnroll * kUnroll;
@@ -999,10 +1007,10 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     // latency: with 5 warps per sub-partition the test loop is latency-bound)
                     constexpr int TI = box_test_ilp(D);
                     unsigned live = 0u;   // slabs of the segment (bit k = records lo + k*SL ...) the brick can reach
-                    if (PRUNE) {
+                    if (slab_cull) {
                         const int ns = (hi - lo + SL - 1) / SL;        // <= 32 (P.seg <= 32 * SL)
                         bool reach = lane < ns;
-                        if (P.slab_cull && reach) {
+                        if (reach) {
                             const float *sb = slabbox + (size_t)(lo / SL + lane) * 2 * D;
                             float box2 = 0.f;
 #pragma unroll
@@ -1014,9 +1022,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         }
                         live = __ballot_sync(0xffffffffu, reach);
                     }
-                    while (live) {
-                        const int base = lo + (__ffs(live) - 1) * SL;
-                        live &= live - 1u;
+                    for (int base = lo; PRUNE && base < hi; base += SL) {
+                        if (slab_cull && !((live >> ((base - lo) / SL)) & 1u)) continue;
                         RecT rec[TI];
                         bool keep[TI];
 #pragma unroll
@@ -1049,7 +1056,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         if (cnt >= P.flush) {
                             const int nsweep = cnt / P.flush * P.flush;
                             __syncwarp();
-                            if (P.level2) {
+                            if (level2) {
                                 for (int k0 = 0; k0 < nsweep; k0 += UNIT2) sweep_unit(wbuf + k0, UNIT2);
                                 __syncwarp();
                             } else {
@@ -1066,7 +1073,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                                 if (k0 + lane < cnt) wbuf[k0 + lane] = carry_rec;
                                 __syncwarp();
                             }
-                            if (!P.level2) u = bound();
+                            if (!level2) u = bound();
                         }
                     }
                 }
@@ -1132,9 +1139,9 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     // second level of the pruned sweep (per pair of groups); it takes the survivors 32 at a time
     // level2: 0 off, 1 on, 3 on with prefetching two-group sweeps.  Default: on for the wide shape
     // (measured in 5-D with the narrow shape: 2.5 x fewer evaluations executed, 10 % slower)
-    P.level2 = PRUNE ? get_option("level2", sh.minb == 1 ? 3 : 0) : 0;
+    P.level2 = PRUNE && eval_shape_has_level2(MINB) ? get_option("level2", sh.minb == 1 ? 3 : 0) : 0;
     P.l2_bypass = get_option("l2_bypass", 7);
-    P.slab_cull = PRUNE && get_option("slab_cull", sh.minb == 1 ? 1 : 0) != 0;   // (narrow shape in 5-D: 5 % slower with it)
+    P.slab_cull = PRUNE && eval_shape_has_level2(MINB) && get_option("slab_cull", sh.minb == 1 ? 1 : 0) != 0;   // (narrow shape in 5-D: 5 % slower with it)
     constexpr int SL = 32 * box_test_ilp(D);     // records per unit of the second level = per slab of the tile
     if (P.level2) {
         if (get_option("flush", 0) <= 0) P.flush = SL;
@@ -1241,6 +1248,12 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
     if (sh.minb == kMediumCtas) {
         if (prune) return launch_eval_shape<D, true, kMediumWarps, kMediumCtas>(P, sh, st);
         return launch_eval_shape<D, false, kMediumWarps, kMediumCtas>(P, sh, st);
+    }
+    if (prune && get_option("narrow_ctas", kNarrowCtas) == 4) {
+        // experiment: 4 CTAs of 4 warps per SM (128 registers per thread) instead of 5 (96)
+        EvalShape sh2 = sh;
+        sh2.minb = 4;
+        return launch_eval_shape<D, true, kNarrowWarps, 4>(P, sh2, st);
     }
     if (prune) return launch_eval_shape<D, true, kNarrowWarps, kNarrowCtas>(P, sh, st);
     return launch_eval_shape<D, false, kNarrowWarps, kNarrowCtas>(P, sh, st);
