@@ -36,6 +36,7 @@ One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement")
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -496,17 +497,24 @@ def run_cuda(args):
     E = exh["evals_per_step"]
 
     # ---- end to end through the public API --------------------------------------------------
+    e2e_call_walls = []      # per-call walls of every e2e_wall() run (diagnostic, rank-local)
+
     def e2e_wall(steps, **env):
         for k, v in env.items():
             os.environ[k] = v
         try:
-            fb.flood_complex(job.host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)  # warm-up
+            for _ in range(2):                                                    # warm-up
+                fb.flood_complex(job.host_pts.to(dev, non_blocking=True), n_lms, points_per_edge=ppe)
+            gc.collect()     # a full collection of the benchmark's own garbage must not land in a timed call
             barrier()
             t0 = time.perf_counter()
+            marks = [t0]
             for _ in range(steps):
                 dpts = job.host_pts.to(dev, non_blocking=True)                   # H2D from pinned memory
                 res = fb.flood_complex(dpts, n_lms, points_per_edge=ppe)        # includes D2H of the values
+                marks.append(time.perf_counter())
             barrier()
+            e2e_call_walls.append([round(b - a, 5) for a, b in zip(marks[:-1], marks[1:])])
             return reduce_max((time.perf_counter() - t0) / steps), len(res)
         finally:
             for k in env:
@@ -618,7 +626,7 @@ def run_cuda(args):
             "e2e": {"value": E / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * dim * 4 * world),
                     "d2h_bytes_per_step": int((job.S * (2 ** job.K - 1) * 4 + n_lms * dim * 4) * world),
-                    "flood_complex_wall_s": e2e_s, "steps": e2e_steps,
+                    "flood_complex_wall_s": e2e_s, "steps": e2e_steps, "call_walls_s": e2e_call_walls[0],
                     "path": "public API, default (exactly pruned) sweep",
                     "exhaustive": {"value": E / e2e_exh_s, "flood_complex_wall_s": e2e_exh_s},
                     "single_gpu_wall_s": e2e_single_s,

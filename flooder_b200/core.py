@@ -22,13 +22,15 @@ import torch
 from . import _native
 from . import distributed as fdist
 from .bricks import brick_order
-from .simplex_tree import FaceTable, SimplexTree, delaunay_complex
+from .simplex_tree import FaceTable, SimplexTree, delaunay_complex, face_keys
 
 _SUPPORTED_DTYPES = (torch.float32, torch.float64)
 
 # Optional stage timing of flood_complex (diagnostics; adds a device synchronisation per stage and
 # therefore removes the host/device overlap -- never enabled inside a timed benchmark region).
 PROFILE_STAGES = os.environ.get("FLOODER_B200_PROFILE", "0") == "1"
+# PROFILE_STAGES = "host": host-side time per stage without the synchronisations (the overlap stays;
+# a stage that waits for the device shows the wait)
 last_stage_seconds: Dict[str, float] = {}
 
 
@@ -40,7 +42,8 @@ class _Stage:
         if PROFILE_STAGES:
             import time
 
-            torch.cuda.synchronize()
+            if PROFILE_STAGES != "host":
+                torch.cuda.synchronize()
             self.t0 = time.perf_counter()
         return self
 
@@ -48,7 +51,8 @@ class _Stage:
         if PROFILE_STAGES:
             import time
 
-            torch.cuda.synchronize()
+            if PROFILE_STAGES != "host":
+                torch.cuda.synchronize()
             last_stage_seconds[self.name] = last_stage_seconds.get(self.name, 0.0) + time.perf_counter() - self.t0
         return False
 
@@ -498,6 +502,10 @@ def flood_complex(
     with _Stage("face_table"):
         table = FaceTable(cells, n_vertices=lms32.shape[0])
         values = table.nan_values()       # NaN = not assigned (simplices above max_dimension)
+    key_lists = None
+    if pending is not None and gudhi_tree is None:
+        with _Stage("face_table"):
+            key_lists = face_keys(table.faces)      # value-independent part of the result, built while the GPU works
     if pending is not None:
         with _Stage("d2h_scatter"):
             _scatter_face_values(table, pending.cpu().numpy(), values)
@@ -529,11 +537,11 @@ def flood_complex(
         # of coface samples, and the minimum over cofaces preserves that); everything else goes
         # through make_filtration_non_decreasing like the reference (core.py:280)
         monotone = pending is not None
-        return _write_back(table, values, gudhi_tree, return_simplex_tree, monotone)
+        return _write_back(table, values, gudhi_tree, return_simplex_tree, monotone, key_lists)
 
 
 def _write_back(table: FaceTable, values: Dict[int, np.ndarray], gudhi_tree, return_simplex_tree: bool,
-                monotone: bool = False):
+                monotone: bool = False, key_lists: Optional[Dict[int, list]] = None):
     """Reference ``core.py:278-288``: assign the values, make the filtration non-decreasing, return
     the tree or ``{tuple(simplex): value}``.  With gudhi the container is gudhi's own tree (the
     reference's contract); otherwise the array-backed stand-in."""
@@ -549,7 +557,7 @@ def _write_back(table: FaceTable, values: Dict[int, np.ndarray], gudhi_tree, ret
         return dict((tuple(simplex), filtr) for (simplex, filtr) in stree.get_simplices())
     if not monotone:
         table.make_non_decreasing(values)
-    stree = SimplexTree.from_arrays(table.faces, values)
+    stree = SimplexTree.from_arrays(table.faces, values, keys=key_lists)
     if return_simplex_tree:
         return stree
-    return stree.to_flat_dict()
+    return stree._f          # the tree is dropped: hand its dictionary over instead of copying it

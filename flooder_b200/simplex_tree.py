@@ -166,12 +166,15 @@ class SimplexTree(PersistenceMixin):
         return st
 
     @classmethod
-    def from_arrays(cls, faces: Dict[int, np.ndarray], values: Dict[int, np.ndarray]) -> "SimplexTree":
+    def from_arrays(cls, faces: Dict[int, np.ndarray], values: Dict[int, np.ndarray],
+                    keys: Optional[Dict[int, list]] = None) -> "SimplexTree":
+        """``keys`` (optional): the key tuples per dimension as ``face_keys`` builds them -- they do
+        not depend on the values, so a caller waiting for the device can prepare them meanwhile."""
         st = cls()
+        if keys is None:
+            keys = face_keys(faces)
         for k in sorted(faces):
-            # zip over the columns builds the key tuples directly (no intermediate row lists)
-            cols = [faces[k][:, j].tolist() for j in range(faces[k].shape[1])]
-            st._f.update(zip(zip(*cols), values[k].tolist()))
+            st._f.update(zip(keys[k], values[k].tolist()))
         return st
 
     def insert(self, simplex: Iterable[int], filtration: float = 0.0) -> bool:
@@ -264,6 +267,16 @@ class SimplexTree(PersistenceMixin):
         """``{simplex: value}`` as ``flood_complex`` returns it (insertion order: by dimension, then
         lexicographic -- the order of ``get_simplices`` for a tree built by ``from_arrays``)."""
         return dict(self._f)
+
+
+def face_keys(faces: Dict[int, np.ndarray]) -> Dict[int, list]:
+    """Key tuples of the simplices per dimension (zip over the columns builds the tuples directly,
+    no intermediate row lists)."""
+    out = {}
+    for k in sorted(faces):
+        cols = [faces[k][:, j].tolist() for j in range(faces[k].shape[1])]
+        out[k] = list(zip(*cols))
+    return out
 
 
 def delaunay_complex(landmarks: np.ndarray):
