@@ -109,10 +109,12 @@ int flood_bounding_balls_f32(const float *verts, int64_t S, int K, int d, float 
  *
  * By default (option "prune" = 1) the sweep is pruned exactly: the samples are handled in bricks
  * of up to 256; a candidate at least as far from the bounding box of a brick as the brick's largest
- * running minimum is skipped for that brick, after a seed pass over every 32nd record of the
- * candidate stream (option "seed_stride") has given every sample a finite bound.  The result is
- * bit-identical to the exhaustive sweep ("prune" = 0); fewer evaluations are executed, E still
- * counts the reference's ball rule.  The number of evaluations actually executed is left as a
+ * running minimum is skipped for that brick, and (option "level2", sample sets of more than two
+ * bricks) the survivors are tested in the same way against the brick's pairs of 32-sample groups
+ * before they are evaluated; a seed pass over every 32nd record of the candidate stream (option
+ * "seed_stride") gives every sample a finite bound first.  The result is bit-identical to the
+ * exhaustive sweep ("prune" = 0); fewer evaluations are executed, E still counts the reference's
+ * ball rule.  The number of evaluations actually executed is left as a
  * uint64 at byte FLOOD_COVER_WS_EXECUTED_OFFSET of `workspace` (device memory).
  * ------------------------------------------------------------------------------------- */
 #define FLOOD_COVER_WS_EXECUTED_OFFSET 16

@@ -283,6 +283,28 @@ def test_brick_order_is_a_compact_permutation():
         return np.mean(vol)
 
     assert mean_box_volume(perm) < 0.25 * mean_box_volume(np.arange(len(w)))
+
+    # the kernel's second pruning level boxes the pairs of groups (0,1), (2,3), ... of a brick:
+    # under the brick order a pair is a compact piece of its brick (mean pair box well below half
+    # of the mean brick box: a brick of 8 groups holds 4 pairs)
+    def mean_pair_volume(order):
+        vol, pos = [], 0
+        for g in groups:
+            for j in range(0, g, 2):
+                idx = order[pos + j * 32: pos + min(j + 2, g) * 32]
+                vol.append(np.prod(x[idx].max(axis=0) - x[idx].min(axis=0)))
+            pos += g * 32
+        return np.mean(vol)
+
+    def mean_brick_volume(order):
+        vol, pos = [], 0
+        for g in groups:
+            idx = order[pos:pos + g * 32]
+            pos += g * 32
+            vol.append(np.prod(x[idx].max(axis=0) - x[idx].min(axis=0)))
+        return np.mean(vol)
+
+    assert mean_pair_volume(perm) < 0.4 * mean_brick_volume(perm)
     # ragged tail, tiny sets, random weights
     for R, gs, per in [(252, [2, 2, 2, 2], 4), (33, [1, 1], 2), (5000, [8] * 19 + [5], 4)]:
         ww = np.random.default_rng(R).dirichlet(np.ones(4), size=R).astype(np.float32)
