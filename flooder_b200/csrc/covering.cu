@@ -19,9 +19,11 @@
 //     holds the brick it works on in registers, tile records are broadcast LDS.128 reads, the
 //     distance is the direct difference form in FP32 (D sub, 1 mul, D-1 fma, 1 min per pair),
 //     issued as packed FP32x2 instructions and 3-input minima (sweep_tile);
-//   * by default the sweep is pruned exactly: per task the records that are at least as far from
-//     the box of the brick's samples as the brick's largest running minimum are skipped, after
-//     a seed pass over a sub-sampled stream has given every sample a finite bound;
+//   * by default the sweep is pruned exactly, on two levels: per task the records that are at
+//     least as far from the box of the brick's samples as the brick's largest running minimum are
+//     skipped (whole slabs of the tile by their bounding box first), the survivors are tested in
+//     the same way against the brick's pairs of groups and swept pair by pair with a prefetching
+//     two-group loop; a seed pass over a sub-sampled stream gives every sample a finite bound first;
 //   * the minima are merged into min_dist2 with an unsigned atomicMin (non-negative floats order
 //     like their bit patterns), because a simplex may be split over several chunks.
 //

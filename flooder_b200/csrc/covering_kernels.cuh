@@ -134,7 +134,8 @@ __device__ __forceinline__ void row_run(const BallCells<G> &b, int row, const Gr
 // The samples of a simplex are cut into bricks of at most kMaxT groups of 32 samples; the bricks
 // of one sample block live in the shared memory of one CTA (nb bricks), more bricks than fit are
 // split into nsb sample blocks.  Two CTA shapes:
-//   wide    20 warps, 1 CTA per SM   (many bricks: every warp starts on its own brick)
+//   wide    20 warps (exhaustive) or 16 warps (pruned), 1 CTA per SM   (many bricks: every warp
+//           starts on its own brick)
 //   medium   8 warps, 2 CTAs per SM  } few bricks: independent CTAs overlap each other's gather and
 //   narrow   4 warps, 5 CTAs per SM  } sweep phases; the warps share the bricks segment by segment
 constexpr int kMaxT = 8;            // sample groups per brick (register-resident while swept)
@@ -561,15 +562,18 @@ __device__ __forceinline__ void sweep_records(const typename Rec<D>::type *recs,
 //           shared memory with atomicMin), so the inner loop is sweep_tile: broadcast LDS.128 of
 //           the records, packed FP32x2 arithmetic, FMNMX3.
 //
-// PRUNE (default) skips work exactly: per task the warp tests the segment's records, 32 at a
-// time, against the bounding box of the brick's samples -- a record at least as far from the box
-// as the brick's largest running minimum u cannot lower any minimum -- and collects the survivors
-// in a per-warp buffer that is swept P.flush (32) records at a time.  u only shrinks, so a skip
-// stays justified; the minima are bit-identical to the exhaustive sweep
-// (tests/test_gpu_kernels.py::test_pruning_is_exact).  This is the "tighter candidate rule" of
-// the unit of work E is still counted by the reference's ball rule, fewer
-// evaluations are executed.  The same bound, taken over all bricks of the CTA, culls records
-// before they enter the tile.
+// PRUNE (default) skips work exactly: per task the warp tests the segment's records, a slab of
+// 32 * box_test_ilp(D) at a time, against the bounding box of the brick's samples -- a record at
+// least as far from the box as the brick's largest running minimum u cannot lower any minimum --
+// and collects the survivors in a per-warp buffer (slabs whose own bounding box is out of reach are
+// skipped unread: slab_cull).  The buffer is swept P.flush records at a time; in the wide shape
+// (level2) through a second test against the boxes and bounds of the brick's pairs of groups
+// (sweep_unit): per pair the survivors are compacted once more and swept with the two-group loop.
+// u and the pair bounds only shrink, so a skip stays justified; the minima are bit-identical to
+// the exhaustive sweep (tests/test_gpu_kernels.py::test_pruning_is_exact, test_covering_options).
+// This is the "tighter candidate rule" of SURVEY.md section 8(f2): the unit of work E is still
+// counted by the reference's ball rule, fewer evaluations are executed.  The same bound, taken over
+// all bricks of the CTA, culls records before they enter the tile.
 template <int D, bool PRUNE, int MAXW, int MINB>
 __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const CoverParams P) {
     using RecT = typename Rec<D>::type;

@@ -143,6 +143,12 @@ def test_face_table_matches_dict_tree(n_vertices):
     st = SimplexTree.from_arrays(table.faces, values)
     for (s, f), (s2, f2) in zip(st.get_simplices(), ref.get_simplices()):
         assert s == s2 and f == f2
+    # keys prepared ahead of the values (flood_complex builds them while the GPU works) give the
+    # same tree, in the same insertion order
+    from flooder_b200.simplex_tree import face_keys
+
+    st2 = SimplexTree.from_arrays(table.faces, values, keys=face_keys(table.faces))
+    assert list(st2.to_flat_dict().items()) == list(st.to_flat_dict().items())
 
 
 @pytest.mark.parametrize("name", ["virus", "coral", "lockwasher"])
