@@ -218,7 +218,11 @@ def test_covering_options(ext, option, value):
 
 
 @pytest.mark.parametrize("kind,n,d,ppe", [("torus", 60_000, 3, 30), ("gauss", 50_000, 3, 12), ("uniform", 20_000, 2, 40),
-                                         ("uniform", 20_000, 5, 4)])
+                                         ("uniform", 20_000, 5, 4),
+                                         # wide shape (more than two bricks: second pruning level) in 2-D with two
+                                         # sample blocks, 4-D, and with the 32-byte records of 5-D / 6-D
+                                         ("uniform", 20_000, 2, 130), ("uniform", 20_000, 4, 10),
+                                         ("uniform", 15_000, 5, 8), ("uniform", 10_000, 6, 7)])
 def test_pruning_is_exact(ext, kind, n, d, ppe):
     """Pruned sweep (with and without the seed pass) == exhaustive sweep, bit for bit, and the
     work counters are unchanged; the pruned modes execute fewer evaluations."""
