@@ -51,6 +51,7 @@ struct CoverParams {
     int slab_cull;           // pruned sweep: whole slabs of tile records are skipped by their bounding box
     int l2_bypass;           // second level: units whose pair-survivor share is >= l2_bypass/8 take the whole-brick sweep
     int off_slab;            // shared-memory offset of the slab boxes
+    int off_pairbox;         // shared-memory offset of the pair boxes (16-byte aligned)
     int wbuf_stride;         // records of per-warp scratch (survivor buffer + second-level buffer)
     // dynamic shared memory layout (byte offsets; tile at 0)
     int off_stage, off_wbuf, off_bricks, off_misc, off_runs;
@@ -599,7 +600,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
     float *sbox = reinterpret_cast<float *>(smem_raw + P.off_misc);           // [nb][2D]
     unsigned *ub = reinterpret_cast<unsigned *>(sbox + nb * 2 * D);           // [nb] largest minimum per brick
     int *cursor = reinterpret_cast<int *>(ub + nb);                           // [nb] next unclaimed segment
-    float *sbox2 = reinterpret_cast<float *>(cursor + nb);                    // [nb][kMaxT/2][2D] boxes of the pairs of groups
+    constexpr int DP = (D + 3) / 4 * 4;        // padded row of a pair box (16-byte loads)
+    float *sbox2 = reinterpret_cast<float *>(smem_raw + P.off_pairbox);       // [nb][kMaxT/2][2][DP] boxes of the pairs of groups
     int *run_start = reinterpret_cast<int *>(smem_raw + P.off_runs);
     __shared__ int warp_sums[32];
     __shared__ int s_fill;
@@ -728,8 +730,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             phi[a] = fmaxf(phi[a], __shfl_xor_sync(0xffffffffu, phi[a], o));
                         }
                         if (L2 && lane == 0) {
-                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + a] = plo[a];
-                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * D + D + a] = phi[a];
+                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * DP + a] = plo[a];
+                            sbox2[((size_t)b * (kMaxT / 2) + (t >> 1)) * 2 * DP + DP + a] = phi[a];
                         }
                         lo[a] = fminf(lo[a], plo[a]);
                         hi[a] = fmaxf(hi[a], phi[a]);
@@ -840,28 +842,39 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                 };
                 constexpr int TI2 = box_test_ilp(D);       // records per lane in a unit
                 constexpr int UNIT2 = 32 * TI2;
+                const float4 *pbox = nullptr;   // boxes of the pairs of the brick in registers (set with the brick)
                 auto sweep_unit = [&](const RecT *src, int n_u) {
                     RecT rec[TI2];
+                    float q[TI2][D];
+                    bool inr[TI2];
                     unsigned mk[NP][TI2];
 #pragma unroll
                     for (int v = 0; v < TI2; ++v) {
-                        const bool inr = lane + 32 * v < n_u;
-                        rec[v] = src[inr ? lane + 32 * v : 0];
-                        float q[D];
-                        rec_unpack<D>(rec[v], q);
+                        inr[v] = lane + 32 * v < n_u;
+                        rec[v] = src[inr[v] ? lane + 32 * v : 0];
+                        rec_unpack<D>(rec[v], q[v]);
+                    }
+                    // every pair unconditionally: an empty pair (brick with fewer groups) keeps an
+                    // inverted box, which nothing is near, and a bound of 0
 #pragma unroll
-                        for (int j = 0; j < NP; ++j) {
-                            mk[j][v] = 0u;
-                            if (2 * j < nt) {
-                                const float *bx = sbox2 + ((size_t)b * NP + j) * 2 * D;
-                                float box2 = 0.f;
+                    for (int j = 0; j < NP; ++j) {
+                        float lo[DP], hi[DP];
 #pragma unroll
-                                for (int a = 0; a < D; ++a) {
-                                    const float e = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[D + a]), 0.f);
-                                    box2 = fmaf(e, e, box2);
-                                }
-                                mk[j][v] = __ballot_sync(0xffffffffu, inr && box2 * 0.9999f <= uj[j]);
+                        for (int a4 = 0; a4 < DP / 4; ++a4) {
+                            const float4 l4 = pbox[j * (2 * DP / 4) + a4];
+                            const float4 h4 = pbox[j * (2 * DP / 4) + DP / 4 + a4];
+                            lo[4 * a4] = l4.x; lo[4 * a4 + 1] = l4.y; lo[4 * a4 + 2] = l4.z; lo[4 * a4 + 3] = l4.w;
+                            hi[4 * a4] = h4.x; hi[4 * a4 + 1] = h4.y; hi[4 * a4 + 2] = h4.z; hi[4 * a4 + 3] = h4.w;
+                        }
+#pragma unroll
+                        for (int v = 0; v < TI2; ++v) {
+                            float box2 = 0.f;
+#pragma unroll
+                            for (int a = 0; a < D; ++a) {
+                                const float e = fmaxf(fmaxf(lo[a] - q[v][a], q[v][a] - hi[a]), 0.f);
+                                box2 = fmaf(e, e, box2);
                             }
+                            mk[j][v] = __ballot_sync(0xffffffffu, inr[v] && box2 * 0.9999f <= uj[j]);
                         }
                     }
                     {
@@ -999,6 +1012,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             u = bound();
 #pragma unroll
                             for (int j = 0; j < NP; ++j) uj[j] = pair_bound(j);
+                            pbox = reinterpret_cast<const float4 *>(sbox2 + (size_t)b * NP * 2 * DP);
                         }
                         have = true;
                     }
@@ -1154,12 +1168,14 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     P.wbuf_stride = P.flush + SL + (P.level2 ? SL + kUnroll : 0);
     const size_t wbuf = PRUNE ? (size_t)sh.W * P.wbuf_stride * sizeof(RecT) : 0;
     const size_t bricks = (size_t)sh.nb * brick_bytes(D);
-    const size_t misc = ((size_t)sh.nb * (2 * D + 2 + (kMaxT / 2) * 2 * D) * 4 + 15) / 16 * 16;
+    constexpr int DPh = (D + 3) / 4 * 4;
+    const size_t misc = ((size_t)sh.nb * (2 * D + 2) * 4 + 15) / 16 * 16;
+    const size_t pairbox = (size_t)sh.nb * (kMaxT / 2) * 2 * DPh * 4;
     const size_t runs = ((size_t)(2 * NT + 1) * sizeof(int) + 15) / 16 * 16;
     // the staging rings are live only while gathering, the survivor buffers only while sweeping:
     // they share one region
     const size_t scratch = staging > wbuf ? staging : wbuf;
-    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + scratch + bricks + misc + runs + (P.slab_cull ? 16 + 2 * D * 4 : 0);
+    const size_t fixed = (size_t)kUnroll * sizeof(RecT) + scratch + bricks + misc + pairbox + runs + (P.slab_cull ? 16 + 2 * D * 4 : 0);
     const long long budget = (long long)(227 * 1024) / sh.minb - 2048;   // static shared memory + per-CTA reserve
     // a tile record costs its bytes plus its share of a slab box
     long long cap = (budget - (long long)fixed) * SL / ((long long)sizeof(RecT) * SL + (P.slab_cull ? 2 * D * 4 : 0));
@@ -1188,6 +1204,7 @@ int launch_eval_shape(CoverParams &P, const EvalShape &sh, cudaStream_t st) {
     P.off_wbuf = (int)o;    o += scratch;
     P.off_bricks = (int)o;  o += bricks;
     P.off_misc = (int)o;    o += misc;
+    P.off_pairbox = (int)o; o += pairbox;
     P.off_runs = (int)o;    o += runs;
     P.off_slab = (int)o;
     if (P.slab_cull) o += ((size_t)(cap / SL + 1) * 2 * D * 4 + 15) / 16 * 16;
