@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                     // box test, two records per lane and trip (independent chains hide each other's
                     // latency: with 5 warps per sub-partition the test loop is latency-bound)
                     constexpr int TI = box_test_ilp(D);
-                    unsigned live = 0u;   // slabs of the segment (bit k = records lo + k*SL ...) the brick can reach
+                    unsigned live = 0xffffffffu;   // slabs of the segment (bit k = records lo + k*SL ...) the brick can reach
                     if (slab_cull) {
                         const int ns = (hi - lo + SL - 1) / SL;        // <= 32 (P.seg <= 32 * SL)
                         bool reach = lane < ns;
@@ -1040,8 +1040,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                         }
                         live = __ballot_sync(0xffffffffu, reach);
                     }
-                    for (int base = lo; PRUNE && base < hi; base += SL) {
-                        if (slab_cull && !((live >> ((base - lo) / SL)) & 1u)) continue;
+                    for (int base = lo, k = 0; PRUNE && base < hi; base += SL, ++k) {
+                        if (!((live >> k) & 1u)) continue;
                         RecT rec[TI];
                         bool keep[TI];
 #pragma unroll
@@ -1072,7 +1072,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) cover_eval_kernel(const Cover
                             cnt += __popc(mask[v]);
                         }
                         if (cnt >= P.flush) {
-                            const int nsweep = cnt / P.flush * P.flush;
+                            int nsweep = P.flush;          // whole multiples of P.flush (at most a few: no division)
+                            while (nsweep + P.flush <= cnt) nsweep += P.flush;
                             __syncwarp();
                             if (level2) {
                                 for (int k0 = 0; k0 < nsweep; k0 += UNIT2) sweep_unit(wbuf + k0, UNIT2);
