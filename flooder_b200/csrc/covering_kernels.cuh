@@ -147,9 +147,9 @@ constexpr int kMediumCtas = 2;
 constexpr int kNarrowWarps = 4;
 constexpr int kNarrowCtas = 5;
 constexpr int kMaxBricks = 20;      // bricks per CTA (<= 32: one lane per brick when stealing)
-// CTAs per SM of the shapes whose pruned kernel carries the second-level code (wide; the
-// experimental 4 x 4-warp narrow shape)
-__host__ __device__ constexpr bool eval_shape_has_level2(int minb) { return minb == 1 || minb == 4; }
+// CTAs per SM of the shapes whose pruned kernel carries the second-level code (the wide shape; a
+// 4 x 4-warp narrow shape with 128 registers was measured with it and dropped: r2_sweeps.md r2p-6)
+__host__ __device__ constexpr bool eval_shape_has_level2(int minb) { return minb == 1; }
 
 struct EvalShape {
     int W;        // warps per CTA
@@ -1254,28 +1254,18 @@ int dispatch_eval(CoverParams &P, int64_t R, cudaStream_t st) {
         // registers); the pruned sweep is a chain of short dependent phases (box tests, compaction,
         // two-group sweeps) that the compiler schedules much better with 128 registers: 16 warps
         // (measured: 20 warps 52 ms, 16 warps 42.6 ms, 12 warps 43.5 ms on torus 1 M / 1 k).
-        const int ww = get_option("wide_warps", prune ? kWidePrunedWarps : kWideWarps);
-        if (ww == 16 || ww == 12) {
+        // (20, 18, 14 and 12 warps for the pruned sweep and 16 for the exhaustive one were measured too
+        // and are not compiled in: profiles/r2_sweeps.md, r2p-3, r2p-4 and r2p-7.)
+        if (prune) {
             EvalShape sh2 = sh;
-            if (sh2.W > ww) sh2.W = ww;
-            if (ww == 16) {
-                if (prune) return launch_eval_shape<D, true, 16, 1>(P, sh2, st);
-                return launch_eval_shape<D, false, 16, 1>(P, sh2, st);
-            }
-            if (prune) return launch_eval_shape<D, true, 12, 1>(P, sh2, st);
+            if (sh2.W > kWidePrunedWarps) sh2.W = kWidePrunedWarps;
+            return launch_eval_shape<D, true, kWidePrunedWarps, 1>(P, sh2, st);
         }
-        if (prune) return launch_eval_shape<D, true, kWideWarps, 1>(P, sh, st);
         return launch_eval_shape<D, false, kWideWarps, 1>(P, sh, st);
     }
     if (sh.minb == kMediumCtas) {
         if (prune) return launch_eval_shape<D, true, kMediumWarps, kMediumCtas>(P, sh, st);
         return launch_eval_shape<D, false, kMediumWarps, kMediumCtas>(P, sh, st);
-    }
-    if (prune && get_option("narrow_ctas", kNarrowCtas) == 4) {
-        // experiment: 4 CTAs of 4 warps per SM (128 registers per thread) instead of 5 (96)
-        EvalShape sh2 = sh;
-        sh2.minb = 4;
-        return launch_eval_shape<D, true, kNarrowWarps, 4>(P, sh2, st);
     }
     if (prune) return launch_eval_shape<D, true, kNarrowWarps, kNarrowCtas>(P, sh, st);
     return launch_eval_shape<D, false, kNarrowWarps, kNarrowCtas>(P, sh, st);

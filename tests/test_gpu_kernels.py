@@ -193,14 +193,14 @@ def test_covering_bruteforce(ext, kind, n, d, S, ppe):
 @pytest.mark.parametrize("option,value", [("chunk", 256), ("warps", 8), ("warps", 3), ("warps", 13),
                                           ("tile_cap", 700), ("ctas_per_sm", 1), ("warps", 4), ("rows_per_chunk_factor", 0),
                                           ("points_per_cell", 1), ("points_per_cell", 64),
-                                          ("level2", 0), ("level2", 1), ("slab_cull", 0), ("wide_warps", 20),
-                                          ("wide_warps", 12), ("flush", 128), ("l2_bypass", 0), ("l2_bypass", 9),
+                                          ("level2", 0), ("level2", 1), ("slab_cull", 0),
+                                          ("flush", 128), ("l2_bypass", 0), ("l2_bypass", 9),
                                           ("seg", 64)])
 def test_covering_options(ext, option, value):
     """Chunk splitting (atomicMin merge), other CTA shapes (several sample blocks, uneven
     groups per warp, odd group counts -> scalar leftover path), small tiles, extreme cell
     sizes and every variant of the pruned sweep (one / two levels, with and without prefetch,
-    slab culling, whole-brick bypass always / never, 20 / 16 / 12 warps) give the same bits."""
+    slab culling, whole-brick bypass always / never) give the same bits."""
     pts = _cloud("torus", 30000, 3, seed=11)
     g = torch.Generator().manual_seed(5)
     lms = pts[torch.randperm(30000, generator=g)[:40]]
