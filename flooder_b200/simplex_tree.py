@@ -10,6 +10,8 @@ the same simplex sets as gudhi/CGAL on every fixture the reference ships (tests/
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 import itertools
 import math
 from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
@@ -76,6 +78,20 @@ def faces_of_cells(cells: np.ndarray, k: int) -> np.ndarray:
     return np.unique(faces, axis=0)
 
 
+@contextlib.contextmanager
+def _gc_paused():
+    """Building tens of thousands of key tuples triggers a cascade of generational collections
+    (measured: 9.0 ms with, 3.0 ms without, for the 25 k simplices of 1000 landmarks in 3-D); tuples
+    of ints cannot be part of a reference cycle, so the collector is paused while they are made."""
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 class FaceTable:
     """All faces of a pure simplicial complex given by its top cells, as arrays.
 
@@ -113,11 +129,20 @@ class FaceTable:
             key = key * self.base + rows[:, j]
         return key
 
+    def _unpack(self, keys: np.ndarray, k: int) -> np.ndarray:
+        rows = np.empty((len(keys), k), dtype=np.int64)
+        rest = keys
+        for j in range(k - 1, -1, -1):
+            rest, rows[:, j] = np.divmod(rest, self.base)
+        return rows
+
     def _unique(self, rows: np.ndarray):
         k = rows.shape[1]
         if self._packable(k):
-            keys, first, inv = np.unique(self._pack(rows), return_index=True, return_inverse=True)
-            return rows[first], keys, inv.reshape(-1)
+            # (return_index would switch np.unique to a stable merge sort: twice the time; the
+            # unique rows are unpacked from the keys instead)
+            keys, inv = np.unique(self._pack(rows), return_inverse=True)
+            return self._unpack(keys, k), keys, inv.reshape(-1)
         uniq, inv = np.unique(rows, axis=0, return_inverse=True)
         return uniq, None, inv.reshape(-1)
 
@@ -173,8 +198,9 @@ class SimplexTree(PersistenceMixin):
         st = cls()
         if keys is None:
             keys = face_keys(faces)
-        for k in sorted(faces):
-            st._f.update(zip(keys[k], values[k].tolist()))
+        with _gc_paused():
+            for k in sorted(faces):
+                st._f.update(zip(keys[k], values[k].tolist()))
         return st
 
     def insert(self, simplex: Iterable[int], filtration: float = 0.0) -> bool:
@@ -273,9 +299,10 @@ def face_keys(faces: Dict[int, np.ndarray]) -> Dict[int, list]:
     """Key tuples of the simplices per dimension (zip over the columns builds the tuples directly,
     no intermediate row lists)."""
     out = {}
-    for k in sorted(faces):
-        cols = [faces[k][:, j].tolist() for j in range(faces[k].shape[1])]
-        out[k] = list(zip(*cols))
+    with _gc_paused():
+        for k in sorted(faces):
+            cols = [faces[k][:, j].tolist() for j in range(faces[k].shape[1])]
+            out[k] = list(zip(*cols))
     return out
 
 
